@@ -1,0 +1,616 @@
+// Tensor-core convolution kernels for sm_100a: TMA-staged NHWC tiles -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).
+//
+//   tc_conv_kernel  : implicit GEMM  D[pixel, co] = sum_{tap, ci} X[pixel + tap, ci] * Wk[co, tap, ci]
+//                     Forward conv (layers.SNConv2d.forward, BigGAN_PyTorch/layers.py:144-153), its dgrad (same
+//                     kernel, flipped/transposed weight copy), and plain GEMMs (H=1: W plays "rows").
+//                     A tile = 128 output pixels (TW x TH x TN box of the NHWC tensor, one 4-D TMA load per filter
+//                     tap with shifted coordinates; TMA zero-fills the halo => padding costs nothing),
+//                     B tile = BN output channels x cw input channels of one tap. Persistent CTAs, one per SM:
+//                     warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue
+//                     (TMEM -> registers -> bias/residual/activation -> NHWC global). Two TMEM accumulator buffers
+//                     let the epilogue of tile i overlap the main loop of tile i+1.
+//   tc_wgrad_kernel : dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci]   (MN-major UMMA operands read
+//                     directly from the NHWC tensors), all 9 tap accumulators resident in TMEM, split-K over pixel
+//                     ranges with float atomics into the fp32 gradient.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace icgan {
+
+static constexpr int kMaxStages = 12;
+static constexpr int kThreads = 192;
+static constexpr uint32_t kSmemBudget = 227u * 1024u;
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, dims[0] fastest. strides_bytes[i] is the stride of dims[i+1].
+static int make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, uint32_t swizzle_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  ICGAN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim,
+                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ICGAN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu)",
+                static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)(rank > 2 ? dims[2] : 0));
+  return 0;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue helpers
+__device__ __forceinline__ void load8(const void* base, int64_t elem_off, int is_bf16, float (&v)[8]) {
+  if (is_bf16) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + elem_off);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+__device__ __forceinline__ void store8(void* base, int64_t elem_off, int is_bf16, const float (&v)[8]) {
+  if (is_bf16) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + elem_off) = raw;
+  } else {
+    float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + elem_off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward / dgrad
+struct TcConvParams {
+  int B, H, W, Cout;
+  int ksz, pad, taps;
+  int TW, TH, TN;
+  int tiles_w, tiles_h, n_tiles, total_tiles;
+  int BN, cw, chunks, k_iters, stages;
+  uint32_t a_bytes, b_tx, stage_bytes, swz, idesc;
+  int out_bf16, res_bf16, res_shift, act;
+  void* y;
+  const float* bias;
+  const void* res;
+};
+
+struct TileCoord {
+  int w0, h0, n0, co0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  int mt = tile / p.n_tiles;
+  const int tw = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int th = mt % p.tiles_h;
+  const int tb = mt / p.tiles_h;
+  t.w0 = tw * p.TW;
+  t.h0 = th * p.TH;
+  t.n0 = tb * p.TN;
+  t.co0 = nt * p.BN;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dh = tap / p.ksz - p.pad, dw = tap % p.ksz - p.pad;
+          for (int cc = 0; cc < p.chunks; ++cc) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
+            uint8_t* sb = sa + p.a_bytes;
+            mbar_expect_tx(&full[stage], p.a_bytes + p.b_tx);
+            tma_load_4d(sa, &tmA, &full[stage], cc * p.cw, t.w0 + dw, t.h0 + dh, t.n0);
+            tma_load_3d(sb, &tmB, &full[stage], cc * p.cw, tap, t.co0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const int ksteps = p.cw / 16;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+        for (int it = 0; it < p.k_iters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = base + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint64_t da = umma_desc_kmajor(sa, p.swz);
+          const uint64_t db = umma_desc_kmajor(sa + p.a_bytes, p.swz);
+          for (int k = 0; k < ksteps; ++k)  // +32 bytes (16 bf16) along K inside the swizzle atom
+            umma_bf16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = q * 32 + lane;
+    const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int n = t.n0 + nl, h = t.h0 + hl, w = t.w0 + wl;
+      const bool valid = (n < p.B) && (h < p.H) && (w < p.W);
+      const int64_t pix = (static_cast<int64_t>(n) * p.H + h) * p.W + w;
+      int64_t rpix = pix;
+      if (p.res_shift) rpix = (static_cast<int64_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u;
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int co = t.co0 + c + half * 8;
+          if (valid && co < p.Cout) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[half * 8 + j]);
+            if (p.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.res) {
+              float rv[8];
+              load8(p.res, rpix * p.Cout + co, p.res_bf16, rv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += rv[j];
+            }
+            if (p.act == ICGAN_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (p.act == ICGAN_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+            }
+            store8(p.y, pix * p.Cout + co, p.out_bf16, v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci], operands read straight from the NHWC tensors:
+// the reduction index (pixels) is the ROW of each TMA box and channels are contiguous, i.e. both UMMA operands are
+// "MN-major".  A stage holds KP=32 pixels: A = two 64-channel boxes of dY (M = 128 output channels),
+// B = for every filter tap one or more 64-channel boxes of X at the tap-shifted pixel coordinates (halo zero-filled
+// by TMA).  All taps accumulate concurrently into TMEM (tap t at columns [t*CT, (t+1)*CT)), so dY is read once.
+struct TcWgradParams {
+  int Cin, Cout, ksz, pad, taps;
+  int TW, TH, TN;
+  int tiles_w, tiles_h, tiles_b, k_chunks;
+  int co_tiles, ci_tiles, splits;
+  int CT, b_boxes, stages;
+  uint32_t a_bytes, box_bytes, stage_bytes, idesc;
+  float* dwk;
+};
+
+static constexpr int kWgradKP = 32;  // pixels (reduction rows) per pipeline stage
+
+// MN-major SW128 operand: 64-channel column groups `lbo_bytes` apart, 8-pixel row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                const TcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item: (co tile, ci tile, pixel-chunk range)
+  int wi = blockIdx.x;
+  const int split = wi % p.splits;
+  wi /= p.splits;
+  const int ci_t = wi % p.ci_tiles;
+  const int co_t = wi / p.ci_tiles;
+  const int per = (p.k_chunks + p.splits - 1) / p.splits;
+  const int kc_begin = split * per;
+  const int kc_end = min(p.k_chunks, kc_begin + per);
+  const int n_chunks = max(0, kc_end - kc_begin);
+  const int co0 = co_t * 128, ci0 = ci_t * p.CT;
+
+  if (warp == 0) {
+    if (lane == 0 && n_chunks > 0) {
+      tma_prefetch_desc(&tmDy);
+      tma_prefetch_desc(&tmX);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        int t = kc;
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tb = t / p.tiles_h;
+        const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tb * p.TN;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
+        mbar_expect_tx(&full[stage], p.a_bytes + static_cast<uint32_t>(p.taps * p.b_boxes) * p.box_bytes);
+        tma_load_4d(sa, &tmDy, &full[stage], co0, w0, h0, n0);
+        tma_load_4d(sa + p.box_bytes, &tmDy, &full[stage], co0 + 64, w0, h0, n0);
+        uint8_t* sb = sa + p.a_bytes;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dh = tap / p.ksz - p.pad, dw = tap % p.ksz - p.pad;
+          for (int bx = 0; bx < p.b_boxes; ++bx) {
+            tma_load_4d(sb, &tmX, &full[stage], ci0 + bx * 64, w0 + dw, h0 + dh, n0);
+            sb += p.box_bytes;
+          }
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_chunks > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_chunks; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = base + static_cast<uint32_t>(stage) * p.stage_bytes;
+        const uint64_t da = umma_desc_mnmajor(sa, p.box_bytes);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const uint64_t db =
+              umma_desc_mnmajor(sa + p.a_bytes + static_cast<uint32_t>(tap * p.b_boxes) * p.box_bytes, p.box_bytes);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(tap * p.CT);
+#pragma unroll
+          for (int k = 0; k < kWgradKP / 16; ++k)  // 16 pixel rows = 2 swizzle atoms = 2048 bytes per UMMA
+            umma_bf16(d_tmem, da + 128u * k, db + 128u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(&tfull[0]);
+    }
+  } else if (n_chunks > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int tap = 0; tap < p.taps; ++tap) {
+      for (int c = 0; c < p.CT; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(tap * p.CT + c), r);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          float* dst = p.dwk + (static_cast<int64_t>(co) * p.taps + tap) * p.Cin + ci0 + c;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (ci0 + c + j < p.Cin) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// NHWC [P][C] (f32 or bf16) -> [C][P] bf16 through a padded shared-memory tile.
+template <typename T>
+__global__ void nhwc_to_cnhw_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ xT, int64_t P, int C) {
+  __shared__ float tile[32][33];
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t pp = p0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (pp < P && c < C) ? ld_as_float(x, pp * C + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t pp = p0 + threadIdx.x;
+    if (c < C && pp < P) xT[static_cast<int64_t>(c) * P + pp] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+}  // namespace icgan
+
+using namespace icgan;
+
+extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* bias, const void* residual, void* y, int B,
+                               int H, int W, int Cin, int Cout, int ksize, int out_dtype, int res_dtype, int res_shift,
+                               int act, void* stream) {
+  ICGAN_REQUIRE(x && wk && y, "icgan_conv2d_tc: null pointer");
+  ICGAN_REQUIRE(ksize == 1 || ksize == 3, "icgan_conv2d_tc: ksize must be 1 or 3 (got %d)", ksize);
+  ICGAN_REQUIRE(B > 0 && H > 0 && W > 0, "icgan_conv2d_tc: bad shape B=%d H=%d W=%d", B, H, W);
+  ICGAN_REQUIRE(Cin % 16 == 0 && Cin >= 16, "icgan_conv2d_tc: Cin must be a multiple of 16 (got %d)", Cin);
+  ICGAN_REQUIRE(Cout % 8 == 0 && Cout >= 8, "icgan_conv2d_tc: Cout must be a multiple of 8 (got %d)", Cout);
+  ICGAN_REQUIRE(!(res_shift && ((H | W) & 1)), "icgan_conv2d_tc: res_shift needs even H, W");
+
+  TcConvParams p{};
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.ksz = ksize; p.pad = ksize / 2; p.taps = ksize * ksize;
+  p.TW = pow2_floor(W < 128 ? W : 128);
+  p.TH = pow2_floor(H < 128 / p.TW ? H : 128 / p.TW);
+  p.TN = 128 / (p.TW * p.TH);
+  p.tiles_w = ceil_div(W, p.TW);
+  p.tiles_h = ceil_div(H, p.TH);
+  const int tiles_b = ceil_div(B, p.TN);
+  p.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  p.swz = static_cast<uint32_t>(p.cw * 2);
+  p.chunks = Cin / p.cw;
+  p.k_iters = p.taps * p.chunks;
+  if (Cout <= 256) p.BN = (Cout + 15) / 16 * 16;
+  else if (Cout % 256 == 0) p.BN = 256;
+  else if (Cout % 192 == 0) p.BN = 192;
+  else if (Cout % 128 == 0) p.BN = 128;
+  else p.BN = 256;
+  p.n_tiles = ceil_div(Cout, p.BN);
+  p.total_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
+  p.a_bytes = 128u * p.swz;
+  p.b_tx = static_cast<uint32_t>(p.BN) * p.swz;
+  p.stage_bytes = p.a_bytes + ((p.b_tx + 1023u) & ~1023u);
+  const uint32_t tail = 1024u /*align slack*/ + 512u /*barriers*/;
+  int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  ICGAN_REQUIRE(stages >= 2, "icgan_conv2d_tc: tile does not fit shared memory");
+  p.stages = stages;
+  p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.BN));
+  p.out_bf16 = out_dtype == ICGAN_BF16;
+  p.res_bf16 = res_dtype == ICGAN_BF16;
+  p.res_shift = res_shift;
+  p.act = act;
+  p.y = y; p.bias = bias; p.res = residual;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const uint32_t box[4] = {(uint32_t)p.cw, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, p.swz);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)p.taps, (uint64_t)Cout};
+    const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)p.taps * Cin * 2};
+    const uint32_t box[3] = {(uint32_t)p.cw, 1u, (uint32_t)p.BN};
+    int rc = make_tmap_bf16(&tmB, wk, 3, dims, str, box, p.swz);
+    if (rc) return rc;
+  }
+  const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
+  static uint32_t configured = 0;
+  if (smem_bytes > configured) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = kSmemBudget;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  tc_conv_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin,
+                                     int Cout, int ksize, void* stream) {
+  ICGAN_REQUIRE(x && dy && dwk, "icgan_conv2d_wgrad_tc: null pointer");
+  ICGAN_REQUIRE(ksize == 1 || ksize == 3, "icgan_conv2d_wgrad_tc: ksize must be 1 or 3");
+  ICGAN_REQUIRE(Cin % 16 == 0 && Cout % 8 == 0, "icgan_conv2d_wgrad_tc: need Cin%%16==0, Cout%%8==0 (got %d, %d)", Cin,
+                Cout);
+
+  TcWgradParams p{};
+  p.Cin = Cin; p.Cout = Cout; p.ksz = ksize; p.pad = ksize / 2; p.taps = ksize * ksize;
+  p.TW = pow2_floor(W < kWgradKP ? W : kWgradKP);
+  p.TH = pow2_floor(H < kWgradKP / p.TW ? H : kWgradKP / p.TW);
+  p.TN = kWgradKP / (p.TW * p.TH);
+  p.tiles_w = ceil_div(W, p.TW);
+  p.tiles_h = ceil_div(H, p.TH);
+  p.tiles_b = ceil_div(B, p.TN);
+  p.k_chunks = p.tiles_w * p.tiles_h * p.tiles_b;
+  if (p.taps == 1) {
+    p.CT = Cin >= 256 ? 256 : (Cin + 15) / 16 * 16;
+  } else {  // all 9 tap accumulators share the 512 TMEM columns and each tap gets one 64-channel box
+    p.CT = (Cin % 48 == 0) ? 48 : (Cin % 32 == 0 ? 32 : 16);
+  }
+  p.b_boxes = (p.CT + 63) / 64;
+  p.co_tiles = ceil_div(Cout, 128);
+  p.ci_tiles = ceil_div(Cin, p.CT);
+  p.box_bytes = static_cast<uint32_t>(kWgradKP) * 128u;
+  p.a_bytes = 2u * p.box_bytes;
+  p.stage_bytes = p.a_bytes + static_cast<uint32_t>(p.taps * p.b_boxes) * p.box_bytes;
+  const uint32_t tail = 1024u + 512u;
+  int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  ICGAN_REQUIRE(stages >= 2, "icgan_conv2d_wgrad_tc: tile does not fit shared memory");
+  p.stages = stages;
+  p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.CT)) | (1u << 15) | (1u << 16);  // A and B MN-major
+  const int out_tiles = p.co_tiles * p.ci_tiles;
+  int splits = ceil_div(2 * num_sms(), out_tiles);
+  if (splits > p.k_chunks) splits = p.k_chunks;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.dwk = dwk;
+
+  CUtensorMap tmDy, tmX;
+  const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+  {
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    int rc = make_tmap_bf16(&tmDy, dy, 4, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    int rc = make_tmap_bf16(&tmX, x, 4, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
+  static bool configured = false;
+  if (!configured) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = true;
+  }
+  const int grid = out_tiles * p.splits;
+  tc_wgrad_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmDy, tmX, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_nhwc_to_cnhw(const void* x, void* xT, int64_t pixels, int C, int in_dtype, void* stream) {
+  ICGAN_REQUIRE(x && xT && pixels > 0 && C > 0, "icgan_nhwc_to_cnhw: bad arguments");
+  dim3 grid(static_cast<unsigned>((pixels + 31) / 32), static_cast<unsigned>((C + 31) / 32));
+  dim3 block(32, 8);
+  if (in_dtype == ICGAN_BF16)
+    nhwc_to_cnhw_kernel<__nv_bfloat16><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xT), pixels, C);
+  else
+    nhwc_to_cnhw_kernel<float><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(x), static_cast<__nv_bfloat16*>(xT), pixels, C);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
