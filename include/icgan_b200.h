@@ -69,6 +69,82 @@ int icgan_channel_sum(const void* x, float* out, int64_t pixels, int C, int dtyp
 /* NHWC [B,H,W,C] -> channel-major [C][B*H*W] bf16. */
 int icgan_nhwc_to_cnhw(const void* x, void* xT, int64_t pixels, int C, int in_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Spectral normalisation (layers.py:39-61 power_iteration, :98-112 SN.W_) — batched over all SN layers of a network.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* W;  /* [rows, cols] row-major master weight (OIHW flattened / [out,in] / [num_embeddings, dim]) */
+  float* u;        /* [rows]  in/out: the `u0` buffer; overwritten with u' iff update_u (training)            */
+  float* v;        /* [cols]  out: normalised right vector                                                     */
+  float* u_new;    /* [rows]  out: normalised left vector u' that defines sigma (needed by the backward)       */
+  float* sigma;    /* [2]     out: sigma = u'^T W v, 1/sigma                                                   */
+  float* scratch;  /* [2]     workspace                                                                        */
+  int rows, cols;
+} IcganSnLayer;
+
+/* One power-iteration step for n_layers layers (descriptor table in DEVICE memory). max_rows/max_cols size the grid. */
+int icgan_sn_power_iteration(const IcganSnLayer* layers_dev, int n_layers, int max_rows, int max_cols, float eps,
+                             int update_u, void* stream);
+/* W (float32 OIHW) * inv_sigma -> wk_fwd [Cout,k,k,Cin] and/or wk_dgrad [Cin,k,k,Cout] (taps flipped), out_dtype.
+ * inv_sigma_dev NULL = no scaling. ksize=1 covers SNLinear/SNEmbedding ([out,in] stays [out,in]). */
+int icgan_sn_prepare_weight(const float* W, const float* inv_sigma_dev, void* wk_fwd, void* wk_dgrad, int Cout,
+                            int Cin, int ksize, int out_dtype, void* stream);
+/* Gradient of the scaled weight (kernel layout, float32) -> gradient of the master weight (OIHW):
+ *   dW = (G - <G, W/sigma> u' v^T) / sigma       (sigma NULL: plain re-layout). scratch: 1 float. */
+int icgan_sn_weight_grad(const float* G_k, const float* W, const float* u_new, const float* v, const float* sigma,
+                         float* scratch, float* dW, int Cout, int Cin, int ksize, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch norm with per-sample affine (layers.ccbn, layers.py:398-437; layers.bn :485-503), NHWC.
+ * ---------------------------------------------------------------------------------------------- */
+/* Two-pass batch statistics over P = B*H*W pixels: mean, invstd = rsqrt(biased var + eps); running buffers (may be
+ * NULL) updated with momentum and the UNBIASED variance as F.batch_norm does. ws: 2*C floats of workspace. */
+int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, float* ws, float* running_mean,
+                         float* running_var, float* mean, float* invstd, float eps, float momentum, void* stream);
+/* y = act(((x-mean)*invstd) * gain[n,c] + bias[n,c]); gain/bias row stride gain_stride (0 = shared [C] vectors);
+ * relu: fuse ReLU; up: write the nearest-upsampled x2 tensor [B,2H,2W,C] (GBlock, layers.py:543-546). */
+int icgan_bn_apply(const void* x, void* y, const float* mean, const float* invstd, const float* gain,
+                   const float* bias, int gain_stride, int B, int H, int W, int C, int relu, int up, int in_dtype,
+                   int out_dtype, void* stream);
+/* Backward, step 1: s1[n,c] = sum_hw g, s2[n,c] = sum_hw g*xhat, g = dL/d(affine output) after undoing up/relu. */
+int icgan_bn_bwd_reduce(const void* x, const void* dy, const float* mean, const float* invstd, const float* gain,
+                        const float* bias, int gain_stride, float* s1, float* s2, int B, int H, int W, int C, int relu,
+                        int up, int x_dtype, int dy_dtype, void* stream);
+/* Backward, step 2: dx = invstd * (gain*g - m1[c] - xhat*m2[c]); m1/m2 = batch means of gain*g and gain*g*xhat
+ * (zeros in eval mode). dx has dy's dtype. */
+int icgan_bn_bwd_apply(const void* x, const void* dy, void* dx, const float* mean, const float* invstd,
+                       const float* gain, const float* bias, int gain_stride, const float* m1, const float* m2, int B,
+                       int H, int W, int C, int relu, int up, int x_dtype, int dy_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise / pooling (F.relu, torch.tanh backward, nn.AvgPool2d(2), F.max_pool2d, F.interpolate(x2),
+ * D's sum pooling BigGAN.py:624, attention residual layers.py:244).
+ * ---------------------------------------------------------------------------------------------- */
+int icgan_relu(const void* x, void* y, int64_t n, int dtype, void* stream);
+int icgan_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, int ref_dtype, int g_dtype, void* stream);
+int icgan_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, int y_dtype, int g_dtype, void* stream);
+/* out = alpha*a + beta*b (b may be NULL); alpha_dev/beta_dev, when non-NULL, are device scalars used instead. */
+int icgan_axpby(const void* a, const void* b, void* out, float alpha, const float* alpha_dev, float beta,
+                const float* beta_dev, int64_t n, int dtype, void* stream);
+int icgan_dot(const void* a, const void* b, float* out, int64_t n, int dtype, void* stream);
+/* mode 0: y = scale * sum_2x2(x) (+ add) ; mode 1: y = max_2x2(x).  x:[B,2Hout,2Wout,C] -> y:[B,Hout,Wout,C] */
+int icgan_pool2(const void* x, const void* add, void* y, int B, int Hout, int Wout, int C, float scale, int mode,
+                int dtype, void* stream);
+/* mode 0: dx = scale * nearest_up2(dy) ; mode 1: max-pool backward using the forward input xref. */
+int icgan_unpool2(const void* dy, const void* xref, void* dx, int B, int Hout, int Wout, int C, float scale, int mode,
+                  int ref_dtype, int g_dtype, void* stream);
+int icgan_relu_sumpool(const void* x, float* out, int B, int HW, int C, int dtype, void* stream);
+int icgan_relu_sumpool_bwd(const void* x, const float* dh, void* dx, int B, int HW, int C, int dtype, void* stream);
+int icgan_softmax_rows(const void* s, void* p, int64_t rows, int cols, int dtype, void* stream);
+int icgan_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, int cols, int dtype, void* stream);
+
+/* Strided batched GEMM on CUDA cores, float32 accumulate (SNLinear layers.py:164-165; attention bmm layers.py:237-243):
+ * C[b][m][n] = alpha*(alpha_dev?*alpha_dev:1) * sum_k A[b][m][k]*B[b][k][n] + bias[n] + beta*C[b][m][n]; strides in elements. */
+int icgan_gemm(const void* A, const void* B, void* C, int M, int N, int K, int batch, int64_t sam, int64_t sak,
+               int64_t sab, int64_t sbk, int64_t sbn, int64_t sbb, int64_t scm, int64_t scn, int64_t scb, float alpha,
+               const float* alpha_dev, float beta, const float* bias, int a_dtype, int b_dtype, int c_dtype,
+               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

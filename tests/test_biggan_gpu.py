@@ -1,0 +1,118 @@
+"""Whole-network parity on the GPU: the B200 Generator/Discriminator/G_D against (i) golden vectors frozen from the
+live reference and (ii) the CPU oracle re-run on the same inputs; float32 parity mode and bf16 throughput mode."""
+import pytest
+import torch
+
+from oracle import biggan_oracle as O
+from tests.helpers import load_golden, make_models, rel_l2
+
+pytestmark = pytest.mark.gpu
+CASES = ["ic64_tiny", "cc32_tiny"]
+# images: BASELINE.json bar (<= 1e-3 max-abs vs the fp32 reference) holds in parity mode; bf16 mode has its own bar.
+IMG_TOL = {torch.float32: 1e-3, torch.bfloat16: 6e-2}
+GRAD_TOL = {torch.float32: 5e-3, torch.bfloat16: 0.15}
+
+
+def _dev(t, dev):
+    return None if t is None else t.to(dev)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+def test_generator_eval_matches_reference(cuda_device, name, cdt):
+    cfg, meta, fx = load_golden(name)
+    G, D, _, _ = make_models(cfg, cuda_device, cdt, meta["seed"])
+    G.eval()
+    with torch.no_grad():
+        out = G(fx["z"].to(cuda_device), _dev(fx.get("label_g"), cuda_device), fx["feats_g"].to(cuda_device))
+    assert out.shape == fx["G_eval_out"].shape and out.dtype == torch.float32
+    err = (out.cpu() - fx["G_eval_out"]).abs().max().item()
+    print(f"G eval {name} {cdt}: max-abs err vs reference {err:.3e}")
+    assert err <= IMG_TOL[cdt]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+def test_d_phase_matches_reference(cuda_device, name, cdt):
+    from ic_gan_b200.biggan import G_D
+    cfg, meta, fx = load_golden(name)
+    dev = cuda_device
+    G, D, g_sd, d_sd = make_models(cfg, dev, cdt, meta["seed"])
+    G.train(); D.train()
+    for p in G.parameters():
+        p.requires_grad_(False)
+    GD = G_D(G, D)
+    d_fake, d_real = GD(fx["z"].to(dev), _dev(fx.get("label_g"), dev), fx["feats_g"].to(dev), fx["x"].to(dev),
+                        _dev(fx.get("label_r"), dev), fx["feats_r"].to(dev), train_G=False)
+    loss = torch.relu(1.0 - d_real).mean() + torch.relu(1.0 + d_fake).mean()
+    loss.backward()
+    logit_tol = 2e-3 if cdt == torch.float32 else 0.35
+    scale = max(1.0, fx["D_real"].abs().max().item())
+    assert (d_fake.cpu() - fx["D_fake"]).abs().max().item() <= logit_tol * scale
+    assert (d_real.cpu() - fx["D_real"]).abs().max().item() <= logit_tol * scale
+    # buffers after one training forward: u0 / sv0 / BN running statistics
+    for key in [k for k in fx if k.startswith("buf_after_Dphase/")]:
+        net, k = key[len("buf_after_Dphase/"):].split(".", 1)
+        got = dict((G if net == "G" else D).state_dict())[k].cpu()
+        tol = 2e-4 if cdt == torch.float32 else 5e-2
+        assert (got - fx[key]).abs().max().item() <= tol * max(1.0, fx[key].abs().max().item()), key
+    # gradients: full tensors where stored, and against the oracle for every parameter
+    for k, v in d_sd.items():
+        if O.is_param(k, v):
+            v.requires_grad_(True)
+    o_fake, o_real = O.gd_forward(g_sd, d_sd, cfg, fx["z"], fx.get("label_g"), fx["feats_g"], fx["x"],
+                                  fx.get("label_r"), fx["feats_r"])
+    a, b = O.loss_hinge_dis(o_fake, o_real)
+    (a + b).backward()
+    worst = 0.0
+    for k, p in D.named_parameters():
+        ref = d_sd[k].grad
+        if ref.abs().max().item() < 1e-6:  # biases feeding no nonlinearity etc.
+            continue
+        e = rel_l2(p.grad, ref)
+        worst = max(worst, e)
+        assert e <= GRAD_TOL[cdt], f"D grad {k}: rel-L2 {e:.3e}"
+    print(f"D phase {name} {cdt}: worst grad rel-L2 {worst:.3e}")
+    for key in [k for k in fx if k.startswith("D_grad/")]:
+        got = dict(D.named_parameters())[key[len("D_grad/"):]].grad
+        assert rel_l2(got, fx[key]) <= GRAD_TOL[cdt], key
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+def test_g_phase_matches_oracle(cuda_device, name, cdt):
+    from ic_gan_b200.biggan import G_D
+    cfg, meta, fx = load_golden(name)
+    dev = cuda_device
+    G, D, g_sd, d_sd = make_models(cfg, dev, cdt, meta["seed"])
+    G.train(); D.train()
+    for p in D.parameters():
+        p.requires_grad_(False)
+    GD = G_D(G, D)
+    d_fake = GD(fx["z"].to(dev), _dev(fx.get("label_g"), dev), fx["feats_g"].to(dev), train_G=True)
+    (-d_fake.mean()).backward()
+    logit_tol = 2e-3 if cdt == torch.float32 else 0.35
+    scale = max(1.0, fx["G_phase_D_fake"].abs().max().item())
+    assert (d_fake.cpu() - fx["G_phase_D_fake"]).abs().max().item() <= logit_tol * scale
+    for k, v in g_sd.items():
+        if O.is_param(k, v):
+            v.requires_grad_(True)
+    o = O.gd_forward(g_sd, d_sd, cfg, fx["z"], fx.get("label_g"), fx["feats_g"], train_G=True)
+    O.loss_hinge_gen(o).backward()
+    worst = 0.0
+    for k, p in G.named_parameters():
+        ref = g_sd[k].grad
+        if ref is None or p.grad is None:
+            assert ref is None or ref.abs().max().item() == 0 or p.grad is not None, k
+            continue
+        if ref.abs().max().item() < 1e-5 * max(1.0, g_sd[k].abs().max().item()):
+            continue  # conv biases followed by batch norm: analytically zero gradient, pure rounding noise
+        e = rel_l2(p.grad, ref)
+        worst = max(worst, e)
+        assert e <= GRAD_TOL[cdt] * 2, f"G grad {k}: rel-L2 {e:.3e}"
+    print(f"G phase {name} {cdt}: worst grad rel-L2 {worst:.3e}")
+
+
+def test_smoke_step(cuda_device):
+    from tests.helpers import smoke_step
+    smoke_step()

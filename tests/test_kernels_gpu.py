@@ -1,0 +1,175 @@
+"""Per-op parity on the GPU: each autograd op of ic_gan_b200.ops against the same op written in plain fp32 PyTorch
+(the reference's own ATen calls), forward and backward, in parity (fp32) and throughput (bf16) dtypes."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 2e-4, torch.bfloat16: 3e-2}
+
+
+def _close(a, b, tol, what):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    scale = max(1.0, b.abs().max().item())
+    assert err <= tol * scale, f"{what}: max-abs err {err:.3e} (scale {scale:.3g}, tol {tol})"
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 32, 48, 16, 3), (2, 64, 96, 8, 3), (4, 16, 32, 4, 1), (2, 3, 16, 16, 3),
+                                   (2, 16, 3, 16, 3)])
+def test_snconv2d_forward_backward(cuda_device, cdt, shape):
+    from ic_gan_b200.biggan import layers
+    B, cin, cout, H, k = shape
+    torch.manual_seed(0)
+    m = layers.SNConv2d(cin, cout, k, padding=k // 2, eps=1e-6).to(cuda_device)
+    m.compute_dtype = cdt
+    m.train()
+    x = torch.randn(B, cin, H, H, device=cuda_device)
+    u0 = m.u0.clone()
+    xq = x.to(cdt).float() if cdt != torch.float32 else x
+    x1 = xq.clone().requires_grad_(True)
+    y = m(x1)
+    gy = torch.randn_like(y.float())
+    y.float().backward(gy)
+    # plain-PyTorch restatement (layers.py:98-112, :144-153)
+    W = m.weight.detach().clone().requires_grad_(True)
+    Wm = W.reshape(cout, -1)
+    with torch.no_grad():
+        v = F.normalize(u0 @ Wm, eps=1e-6)
+        un = F.normalize(v @ Wm.t(), eps=1e-6)
+    sigma = (v @ Wm.t() @ un.t()).squeeze()
+    x2 = xq.clone().requires_grad_(True)
+    bias = m.bias.detach().clone().requires_grad_(True)
+    yr = F.conv2d(x2, W / sigma, bias, 1, k // 2)
+    yr.backward(gy.to(cdt).float() if cdt != torch.float32 else gy)
+    tol = TOL[cdt]
+    _close(y, yr, tol, "conv fwd")
+    _close(m.u0, un, 1e-5, "u update")
+    _close(m.sv0, sigma.reshape(1), 1e-5, "sv0")
+    _close(x1.grad, x2.grad, tol, "conv dgrad")
+    _close(m.weight.grad, W.grad, tol * 2, "conv wgrad (through sigma)")
+    _close(m.bias.grad, bias.grad, tol * 2, "conv bias grad")
+
+
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("up", [False, True])
+def test_ccbn_relu_up(cuda_device, cdt, up):
+    from ic_gan_b200 import ops
+    torch.manual_seed(1)
+    B, C, H = 4, 32, 8
+    x = torch.randn(B, C, H, H, device=cuda_device) * 2 + 0.5
+    gain = (1 + 0.3 * torch.randn(B, C, device=cuda_device)).requires_grad_(True)
+    bias = (0.3 * torch.randn(B, C, device=cuda_device)).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+    xq = x.to(cdt).float()
+    x1 = _nhwc(xq).to(cdt).requires_grad_(True)
+    y = ops.BNActFn.apply(x1, gain, bias, rm, rv, True, 1e-5, 0.1, True, up, cdt)
+    gy = torch.randn_like(y.float())
+    y.float().backward(gy)
+    x2 = xq.clone().requires_grad_(True)
+    g2, b2 = gain.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+    yr = F.batch_norm(x2, rm2, rv2, None, None, True, 0.1, 1e-5) * g2[:, :, None, None] + b2[:, :, None, None]
+    yr = F.relu(yr)
+    if up:
+        yr = F.interpolate(yr, scale_factor=2)
+    gyr = gy.to(cdt).float().permute(0, 3, 1, 2) if cdt != torch.float32 else gy.permute(0, 3, 1, 2)
+    yr.backward(gyr)
+    tol = TOL[cdt]
+    _close(y.permute(0, 3, 1, 2), yr, tol, "bn fwd")
+    _close(rm, rm2, 1e-5, "running mean")
+    _close(rv, rv2, 1e-5, "running var")
+    _close(x1.grad.permute(0, 3, 1, 2), x2.grad, tol * 2, "bn dx")
+    _close(gain.grad, g2.grad, tol * 4, "bn dgain")
+    _close(bias.grad, b2.grad, tol * 4, "bn dbias")
+
+
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+def test_attention_block(cuda_device, cdt):
+    from ic_gan_b200.biggan import layers
+    import functools
+    torch.manual_seed(2)
+    C, B, H = 64, 2, 16
+    att = layers.Attention(C, functools.partial(layers.SNConv2d, eps=1e-6)).to(cuda_device)
+    for m in att.modules():
+        if isinstance(m, layers.SN):
+            m.compute_dtype = cdt
+    with torch.no_grad():
+        att.gamma.fill_(0.7)
+    att.train()
+    u = {n: getattr(att, n).u0.clone() for n in ("theta", "phi", "g", "o")}
+    x = torch.randn(B, C, H, H, device=cuda_device)
+    xq = x.to(cdt).float()
+    x1 = xq.to(cdt).clone().requires_grad_(True)
+    y = att(x1)
+    gy = torch.randn_like(y.float())
+    y.float().backward(gy)
+
+    def snw(name):
+        W = getattr(att, name).weight.detach()
+        Wm = W.reshape(W.shape[0], -1)
+        v = F.normalize(u[name] @ Wm, eps=1e-6)
+        un = F.normalize(v @ Wm.t(), eps=1e-6)
+        return W / (v @ Wm.t() @ un.t()).squeeze()
+    x2 = xq.clone().requires_grad_(True)
+    theta = F.conv2d(x2, snw("theta"))
+    phi = F.max_pool2d(F.conv2d(x2, snw("phi")), 2)
+    g = F.max_pool2d(F.conv2d(x2, snw("g")), 2)
+    theta = theta.view(B, C // 8, H * H)
+    phi = phi.view(B, C // 8, H * H // 4)
+    g = g.view(B, C // 2, H * H // 4)
+    beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)
+    o = F.conv2d(torch.bmm(g, beta.transpose(1, 2)).view(B, C // 2, H, H), snw("o"))
+    yr = 0.7 * o + x2
+    yr.backward(gy.to(cdt).float() if cdt != torch.float32 else gy)
+    tol = TOL[cdt] * 2
+    _close(y, yr, tol, "attention fwd")
+    _close(x1.grad, x2.grad, tol * 2, "attention dx")
+
+
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+def test_pool_relu_sumpool_linear(cuda_device, cdt):
+    from ic_gan_b200 import ops
+    from ic_gan_b200.biggan import layers
+    torch.manual_seed(3)
+    x = torch.randn(3, 24, 8, 8, device=cuda_device).to(cdt).float()
+    add = torch.randn(3, 24, 4, 4, device=cuda_device).to(cdt).float()
+    x1 = _nhwc(x).to(cdt).requires_grad_(True)
+    a1 = _nhwc(add).to(cdt).requires_grad_(True)
+    y = ops.Pool2Fn.apply(ops.ReluFn.apply(x1), a1, 0.25, 0)
+    h = ops.ReluSumPoolFn.apply(y)
+    mx = ops.Pool2Fn.apply(x1, None, 1.0, 1)
+    (h.sum() * 0.5 + (mx.float() ** 2).sum()).backward()
+    x2, a2 = x.clone().requires_grad_(True), add.clone().requires_grad_(True)
+    yr = F.avg_pool2d(F.relu(x2), 2) + a2
+    hr = F.relu(yr).sum(dim=(2, 3))
+    mr = F.max_pool2d(x2, 2)
+    (hr.sum() * 0.5 + (mr ** 2).sum()).backward()
+    tol = TOL[cdt]
+    _close(y.permute(0, 3, 1, 2), yr, tol, "avgpool+add")
+    _close(h, hr, tol * 4, "relu sumpool")
+    _close(mx.permute(0, 3, 1, 2), mr, tol, "maxpool")
+    _close(x1.grad.permute(0, 3, 1, 2), x2.grad, tol * 4, "dx")
+    _close(a1.grad.permute(0, 3, 1, 2), a2.grad, tol * 4, "dadd")
+    lin = layers.SNLinear(37, 19, eps=1e-6).to(cuda_device)
+    lin.train()
+    u0 = lin.u0.clone()
+    xi = torch.randn(5, 37, device=cuda_device, requires_grad=True)
+    out = lin(xi)
+    out.pow(2).sum().backward()
+    W = lin.weight.detach().clone().requires_grad_(True)
+    v = F.normalize(u0 @ W.detach(), eps=1e-6)
+    un = F.normalize(v @ W.detach().t(), eps=1e-6)
+    sigma = (v @ W.t() @ un.t()).squeeze()
+    xr = xi.detach().clone().requires_grad_(True)
+    outr = F.linear(xr, W / sigma, lin.bias.detach())
+    outr.pow(2).sum().backward()
+    _close(out, outr, 1e-4, "linear fwd")
+    _close(xi.grad, xr.grad, 1e-4, "linear dx")
+    _close(lin.weight.grad, W.grad, 1e-4, "linear dW through sigma")
