@@ -6,6 +6,10 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+# the PyTorch side is the fp32 reference: no TF32 in cuDNN/cuBLAS
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 TOL = {torch.float32: 2e-4, torch.bfloat16: 3e-2}
 
 
