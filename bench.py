@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of one IC-GAN BigGAN G+D training step (BASELINE.json metric) on N B200 GPUs of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W                      (N=1)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W     (the reference algorithm on the host CPU cores)
+
+A "step" is one GAN_training_function.train call (BigGAN_PyTorch/train_fns.py:40-191 semantics: D update on B fake +
+B real, G update on B fake, Adam x2, EMA) over a per-GPU batch of synthetic images and instance features, realised as
+micro-batches with gradient accumulation (BN statistics are per micro-batch, as in the reference).  Weak scaling: every
+rank processes the same per-GPU batch; gradients are averaged with one NCCL all-reduce for D and one for G per step.
+One JSON line is printed by rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline, e2e, clocks).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# forward GFLOP per image (conv + linear + attention bmm, 2*MAC) measured on the reference modules: SURVEY.md §8(d)
+WORKLOADS = {
+    "cc256": dict(name="cc-IC-GAN BigGAN 256x256 (ch96, attn@64, class+instance cond)", resolution=256, ch=96,
+                  attn="64", class_cond=True, G_f=146.43, D_f=74.67, per_gpu_batch=256, micro_batch=32),
+    "ic128": dict(name="IC-GAN BigGAN 128x128 (ch96, attn@64, instance cond)", resolution=128, ch=96, attn="64",
+                  class_cond=False, G_f=42.26, D_f=21.68, per_gpu_batch=256, micro_batch=64),
+    "ic64": dict(name="IC-GAN BigGAN 64x64 (ch64, attn@32, instance cond)", resolution=64, ch=64, attn="32",
+                 class_cond=False, G_f=14.52, D_f=2.23, per_gpu_batch=256, micro_batch=128),
+}
+METRIC = "images/sec G+D step, IC-GAN BigGAN"
+
+
+def model_kwargs(w):
+    return dict(G_ch=w["ch"], D_ch=w["ch"], dim_z=120, resolution=w["resolution"], G_attn=w["attn"], D_attn=w["attn"],
+                n_classes=1000, G_shared=True, shared_dim=128, hier=True, BN_eps=1e-5, SN_eps=1e-6,
+                class_cond=w["class_cond"], instance_cond=True, G_shared_feat=True, shared_dim_feat=512,
+                G_init="ortho", D_init="ortho")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def oracle_step_rate(w, batch, steps, warmup, threads):
+    """images/s of the oracle's train_step (CPU restatement of the reference algorithm) at micro-batch `batch`."""
+    from oracle import biggan_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.BigGANConfig(resolution=w["resolution"], G_ch=w["ch"], D_ch=w["ch"], G_attn=w["attn"], D_attn=w["attn"],
+                         class_cond=w["class_cond"], instance_cond=True)
+    gs, ds = O.state_shapes(cfg)
+    st = O.make_step_state(O.synth_state_dict(gs, 1), O.synth_state_dict(ds, 2), G_lr=4e-5, D_lr=1e-4, ema=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(batch, 3, cfg.resolution, cfg.resolution, generator=g) * 2 - 1
+    feats = torch.nn.functional.normalize(torch.randn(batch, 2048, generator=g), dim=1)
+    y = torch.randint(0, 1000, (batch,), generator=g) if cfg.class_cond else None
+
+    def sample_cond():
+        z = torch.randn(batch, cfg.eff_dim_z, generator=g)
+        f = torch.nn.functional.normalize(torch.randn(batch, 2048, generator=g), dim=1)
+        lab = torch.randint(0, 1000, (batch,), generator=g) if cfg.class_cond else None
+        return z, lab, f
+    for _ in range(warmup):
+        O.train_step(st, cfg, x, y, feats, sample_cond, batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(st, cfg, x, y, feats, sample_cond, batch)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch / dt, dt
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 2 if (args.steps + args.warmup) <= 6 else 1
+    ips, dt = oracle_step_rate(w, batch, args.steps, args.warmup, threads)
+    sample = f"oracle train_step (CPU restatement of train_fns.py:40-191), micro-batch {batch}, fp32, {threads} threads"
+    line = {"impl": "reference", "metric": f"{METRIC} {w['resolution']}x{w['resolution']}", "value": ips,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": w["name"], "micro_batch": batch, "host_threads": threads},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cc256", choices=sorted(WORKLOADS))
+    ap.add_argument("--per-gpu-batch", type=int, default=0)
+    ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.per_gpu_batch:
+        w["per_gpu_batch"] = args.per_gpu_batch
+    if args.micro_batch:
+        w["micro_batch"] = args.micro_batch
+    if args.impl == "reference":
+        return run_reference(args, w)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from ic_gan_b200 import _lib, ops
+    from ic_gan_b200.biggan import G_D, Discriminator, Generator
+    from ic_gan_b200.biggan import train_fns
+    from ic_gan_b200.dist import GradSync
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    cdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    m, Bg = w["micro_batch"], w["per_gpu_batch"]
+    assert Bg % m == 0, "per-GPU batch must be a multiple of the micro-batch"
+    acc = Bg // m
+    kw = model_kwargs(w)
+    torch.manual_seed(1234)
+    G = Generator(no_optim=True, compute_dtype=cdt, **kw).to(dev)
+    D = Discriminator(embedded_optimizer=False, compute_dtype=cdt, **kw).to(dev)
+    G_ema = Generator(no_optim=True, skip_init=True, compute_dtype=cdt, **kw).to(dev)
+    sync = GradSync({"G": G, "D": D}, world)
+    sync.broadcast_params()
+    opt_G = torch.optim.Adam(G.parameters(), lr=4e-5, betas=(0.0, 0.999), weight_decay=0, eps=1e-6, fused=True)
+    opt_D = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.999), weight_decay=0, eps=1e-6, fused=True)
+    GD = G_D(G, D, opt_G, opt_D)
+    ema = train_fns.ema(G, G_ema, 0.9999, 20000)
+    state = {"itr": 0}
+    config = {"toggle_grads": True, "num_D_steps": 1, "num_D_accumulations": acc, "num_G_accumulations": acc,
+              "split_D": False, "ema": True, "D_ortho": 0.0, "G_ortho": 0.0, "DA": False, "DiffAugment": False}
+    R, dim_z, cc = w["resolution"], G.dim_z, w["class_cond"]
+
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    # device-resident real batch + a pool of pre-drawn conditionings (the `value` leg)
+    x_dev = torch.rand(Bg, 3, R, R, device=dev, generator=gen) * 2 - 1
+    f_dev = torch.nn.functional.normalize(torch.randn(Bg, 2048, device=dev, generator=gen), dim=1)
+    y_dev = torch.randint(0, 1000, (Bg,), device=dev, generator=gen) if cc else None
+    pool = 2 * acc
+    z_pool = torch.randn(pool, m, dim_z, device=dev, generator=gen)
+    fg_pool = torch.nn.functional.normalize(torch.randn(pool, m, 2048, device=dev, generator=gen), dim=2)
+    yg_pool = torch.randint(0, 1000, (pool, m), device=dev, generator=gen) if cc else None
+    cursor = [0]
+
+    def sample_dev():
+        i = cursor[0] % pool
+        cursor[0] += 1
+        return (z_pool[i], yg_pool[i], fg_pool[i]) if cc else (z_pool[i], fg_pool[i])
+
+    train_dev = train_fns.GAN_training_function(G, D, GD, ema, state, config, sample_dev, embedded_optimizers=False,
+                                                device=dev, batch_size=m, grad_sync=sync)
+
+    def step_dev():
+        sync.broadcast_buffers()
+        out = train_dev(x_dev, y_dev, f_dev)
+        state["itr"] += 1
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    G.train(); D.train()
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE = [] if rank == 0 else None
+    launches0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    launches = _lib.LAUNCHES - launches0
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = Bg * world / (ms * 1e-3)
+
+    # ---------------- e2e: the same step through the public call with HOST inputs (pinned) and a host read of the losses
+    e2e = None
+    if not args.no_e2e:
+        cpu_gen = torch.Generator().manual_seed(200 + rank)
+        x_host = (torch.rand(Bg, 3, R, R, generator=cpu_gen) * 2 - 1).pin_memory()
+        f_host = torch.nn.functional.normalize(torch.randn(Bg, 2048, generator=cpu_gen), dim=1).pin_memory()
+        y_host = torch.randint(0, 1000, (Bg,), generator=cpu_gen).pin_memory() if cc else None
+        zbuf = torch.empty(m, dim_z).pin_memory()
+        fg_host = torch.nn.functional.normalize(torch.randn(64, m, 2048, generator=cpu_gen), dim=2).pin_memory()
+        yg_host = torch.randint(0, 1000, (64, m), generator=cpu_gen).pin_memory() if cc else None
+        h2d = [0]
+
+        def sample_host():  # host-side draw like data_utils.sample_conditioning_values: z ~ N(0,1) in place, rows of feats
+            i = cursor[0] % 64
+            cursor[0] += 1
+            zbuf.normal_(generator=cpu_gen)
+            h2d[0] += zbuf.numel() * 4 + fg_host[i].numel() * 4 + (yg_host[i].numel() * 8 if cc else 0)
+            return (zbuf, yg_host[i], fg_host[i]) if cc else (zbuf, fg_host[i])
+
+        train_host = train_fns.GAN_training_function(G, D, GD, ema, state, config, sample_host,
+                                                     embedded_optimizers=False, device=dev, batch_size=m,
+                                                     grad_sync=sync)
+
+        def step_host():
+            sync.broadcast_buffers()
+            xd = x_host.to(dev, non_blocking=True)
+            fd = f_host.to(dev, non_blocking=True)
+            yd = y_host.to(dev, non_blocking=True) if cc else None
+            out = train_host(xd, yd, fd)
+            state["itr"] += 1
+            return float(out["G_loss"].item()) + float(out["D_loss_real"].item()) + float(out["D_loss_fake"].item())
+
+        step_host()
+        barrier()
+        h2d[0] = 0
+        e0.record()
+        for _ in range(args.steps):
+            step_host()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        per_step_in = x_host.numel() * 4 + f_host.numel() * 4 + (y_host.numel() * 8 if cc else 0) + h2d[0] // args.steps
+        e2e = {"value": Bg * world / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(per_step_in), "d2h_bytes_per_step": 12}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel from the events recorded INSIDE the timed region
+    pk = peaks()
+    per_kernel = {}
+    for name, flops, a, b in prof:
+        d = per_kernel.setdefault(name, [0.0, 0.0, 0])
+        d[0] += flops
+        d[1] += a.elapsed_time(b) * 1e-3
+        d[2] += 1
+    kinfo = {k: {"launches": v[2], "avg_ms": v[1] / v[2] * 1e3, "tflops": v[0] / v[1] * 1e-12,
+                 "share_of_step": v[1] / (ms * 1e-3 * args.steps)} for k, v in per_kernel.items()}
+    dom = max(per_kernel, key=lambda k: per_kernel[k][1]) if per_kernel else None
+    roofline = None
+    if dom:
+        ach = per_kernel[dom][0] / per_kernel[dom][1] * 1e-12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
+                    "flops_per_launch": per_kernel[dom][0] / per_kernel[dom][2], "kernels": kinfo}
+    f_step = 4 * w["G_f"] + 8 * w["D_f"]  # GF per image, reference step model
+    step_tf = f_step * 1e9 * value / world * 1e-12
+    line = {"metric": f"{METRIC} {R}x{R}", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": w["name"], "per_gpu_batch": Bg, "micro_batch": m, "accumulations": acc,
+                       "global_batch": Bg * world, "parallelism": f"dp{world}", "l2": "inputs larger than L2",
+                       "optimizer": "torch.optim.Adam(fused) x2 + EMA", "step_gflop_per_image": f_step},
+            "roofline": roofline,
+            "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ips, dt = oracle_step_rate(w, 2, 1, 0, threads)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": "1 oracle G+D step (CPU restatement of train_fns.py:40-191), micro-batch 2, "
+                                          f"fp32, {dt:.1f} s, no warm-up"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

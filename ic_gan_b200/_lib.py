@@ -84,7 +84,14 @@ def last_error() -> str:
     return load().icgan_last_error().decode("utf-8", "replace")
 
 
+# kernels launched per entry point (everything else launches exactly one); bench.py reports the running total
+KERNELS_PER_CALL = {"icgan_bn_train_stats": 3, "icgan_sn_power_iteration": 4, "icgan_sn_weight_grad": 2}
+LAUNCHES = 0
+
+
 def call(name: str, *args) -> None:
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {last_error()}")

@@ -18,6 +18,22 @@ from ._lib import call, dt, ptr, stream_ptr
 Tensor = torch.Tensor
 
 
+# When bench.py sets PROFILE to a list, every tensor-core conv launch is bracketed by CUDA events on the launching
+# stream and recorded as (kernel, algorithmic FLOPs, start, end) — the live source of the roofline numbers.
+PROFILE = None
+
+
+def _timed(kernel: str, flops: float, fn):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    PROFILE.append((kernel, flops, e0, e1))
+    return out
+
+
 def _tc_ok(x: Tensor, cin: int, cout: int, k: int) -> bool:
     return x.dtype == torch.bfloat16 and cin % 16 == 0 and cout % 8 == 0 and k in (1, 3)
 
@@ -123,8 +139,7 @@ def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype,
              table_cache["max_cols"], float(eps), 1 if training else 0, stream_ptr())
         if training:  # sv0 is a log-only buffer (layers.py:108-111)
             with torch.no_grad():
-                for s in sn_states:
-                    s.module.sv0.copy_(s.sigma[:1])
+                torch._foreach_copy_([s.module.sv0 for s in sn_states], [s.sigma[:1] for s in sn_states])
     for s in states:
         s.prepare()
         s.fresh = True
@@ -141,8 +156,9 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
     y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
     rdt = dt(residual) if residual is not None else L.F32
     if _tc_ok(x, cin, cout, k) and wk.dtype == torch.bfloat16:
-        call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k, dt(y), rdt,
-             res_shift, act, stream_ptr())
+        _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
+               lambda: call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k,
+                            dt(y), rdt, res_shift, act, stream_ptr()))
     else:
         w32 = wk if wk.dtype == torch.float32 else wk32
         if w32 is None:
@@ -204,7 +220,9 @@ class SNConvFn(torch.autograd.Function):
             G = torch.zeros(cout, k, k, cin, device=dy.device, dtype=torch.float32)
             dyc = dy if dy.dtype == x.dtype else dy.to(x.dtype)
             if x.dtype == torch.bfloat16 and cin % 16 == 0 and cout % 8 == 0:
-                call("icgan_conv2d_wgrad_tc", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, stream_ptr())
+                _timed("tc_wgrad_kernel", 2.0 * B * H * W * cout * cin * k * k,
+                       lambda: call("icgan_conv2d_wgrad_tc", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k,
+                                    stream_ptr()))
             else:
                 call("icgan_conv2d_wgrad_simt", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, 1, k // 2, dt(x),
                      stream_ptr())

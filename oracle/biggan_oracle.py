@@ -385,7 +385,7 @@ def train_step(st: StepState, cfg: BigGANConfig, x: Tensor, y: Optional[Tensor],
             for k, v in st.g_sd.items():
                 st.ema_sd[k].copy_(st.ema_sd[k] * decay + v.detach() * (1 - decay))
     st.itr += 1
-    return {"G_loss": float(g_loss), "D_loss_real": float(l_real), "D_loss_fake": float(l_fake)}
+    return {"G_loss": g_loss.item(), "D_loss_real": l_real.item(), "D_loss_fake": l_fake.item()}
 
 
 # ----------------------------------------------------------------------------- synthetic weights
