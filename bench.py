@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: short warm-up allowed, no e2e/cpu legs "
+                                                       "(a number printed by such a run is never a bench value)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.per_gpu_batch:
@@ -169,7 +171,9 @@ def main():
         w["micro_batch"] = args.micro_batch
     if args.impl == "reference":
         return run_reference(args, w)
-    if args.warmup < 3:
+    if args.ncu:
+        args.no_e2e = args.no_cpu_baseline = True
+    elif args.warmup < 3:
         args.warmup = 3
 
     import torch.distributed as dist
@@ -196,9 +200,13 @@ def main():
     acc = Bg // m
     kw = model_kwargs(w)
     torch.manual_seed(1234)
-    G = Generator(no_optim=True, compute_dtype=cdt, **kw).to(dev)
-    D = Discriminator(embedded_optimizer=False, compute_dtype=cdt, **kw).to(dev)
+    # random-init weights of the named architecture, drawn on the device (N(0, 0.02) = the reference's "N02" init style)
+    G = Generator(no_optim=True, skip_init=True, compute_dtype=cdt, **kw).to(dev)
+    D = Discriminator(embedded_optimizer=False, skip_init=True, compute_dtype=cdt, **kw).to(dev)
     G_ema = Generator(no_optim=True, skip_init=True, compute_dtype=cdt, **kw).to(dev)
+    for net in (G, D):
+        net.init = "N02"
+        net.init_weights()
     sync = GradSync({"G": G, "D": D}, world)
     sync.broadcast_params()
     opt_G = torch.optim.Adam(G.parameters(), lr=4e-5, betas=(0.0, 0.999), weight_decay=0, eps=1e-6, fused=True)
@@ -349,9 +357,10 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        ips, dt = oracle_step_rate(w, 2, 1, 0, threads)
+        cb = 1 if w["resolution"] >= 256 else 2
+        ips, dt = oracle_step_rate(w, cb, 1, 0, threads)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": "1 oracle G+D step (CPU restatement of train_fns.py:40-191), micro-batch 2, "
+                                "sample": f"1 oracle G+D step (CPU restatement of train_fns.py:40-191), micro-batch {cb}, "
                                           f"fp32, {dt:.1f} s, no warm-up"}
     print(json.dumps(line), flush=True)
     if world > 1:

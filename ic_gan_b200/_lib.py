@@ -35,6 +35,8 @@ SIGNATURES = {
     "icgan_conv2d_wgrad_tc": [vp, vp, fp, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_simt": [vp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_simt": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_conv2d_small": [vp, fp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_conv2d_wgrad_small": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_channel_sum": [vp, fp, i64, i32, i32, vp],
     "icgan_nhwc_to_cnhw": [vp, vp, i64, i32, i32, vp],
     "icgan_sn_power_iteration": [vp, i32, i32, i32, f32, i32, vp],
@@ -85,7 +87,7 @@ def last_error() -> str:
 
 
 # kernels launched per entry point (everything else launches exactly one); bench.py reports the running total
-KERNELS_PER_CALL = {"icgan_bn_train_stats": 3, "icgan_sn_power_iteration": 4, "icgan_sn_weight_grad": 2}
+KERNELS_PER_CALL = {"icgan_bn_train_stats": 3, "icgan_sn_power_iteration": 5, "icgan_sn_weight_grad": 2}
 LAUNCHES = 0
 
 

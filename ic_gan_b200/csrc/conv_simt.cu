@@ -182,7 +182,13 @@ __global__ void channel_sum_kernel(const T* __restrict__ x, float* __restrict__ 
   const int64_t r1 = r0 + rows_per_block < P ? r0 + rows_per_block : P;
   for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {
     float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) s += ld_as_float(x, r * C + c);
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      const float a = ld_as_float(x, r * C + c), b = ld_as_float(x, (r + 1) * C + c),
+                  d = ld_as_float(x, (r + 2) * C + c), e = ld_as_float(x, (r + 3) * C + c);
+      s += (a + b) + (d + e);
+    }
+    for (; r < r1; ++r) s += ld_as_float(x, r * C + c);
     atomicAdd(out + c, s);
   }
 }
@@ -258,8 +264,8 @@ extern "C" int icgan_conv2d_wgrad_simt(const void* x, const void* dy, float* dwk
 
 extern "C" int icgan_channel_sum(const void* x, float* out, int64_t P, int C, int dtype, void* stream) {
   ICGAN_REQUIRE(x && out && P > 0 && C > 0, "icgan_channel_sum: bad arguments");
-  int row_blocks = static_cast<int>((P + 511) / 512);
-  if (row_blocks > 4 * num_sms()) row_blocks = 4 * num_sms();
+  int row_blocks = static_cast<int>((P + 63) / 64);
+  if (row_blocks > 24 * num_sms()) row_blocks = 24 * num_sms();
   const int64_t rpb = (P + row_blocks - 1) / row_blocks;
   row_blocks = static_cast<int>((P + rpb - 1) / rpb);
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32));

@@ -32,12 +32,23 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, float* __restrict__ ws,
   const float invP = 1.0f / static_cast<float>(P);
   for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {
     float s = 0.f;
+    int64_t r = r0;
     if (PASS == 1) {
-      for (int64_t r = r0; r < r1; ++r) s += ld_as_float(x, r * C + c);
+      for (; r + 4 <= r1; r += 4) {
+        const float a = ld_as_float(x, r * C + c), b = ld_as_float(x, (r + 1) * C + c),
+                    d = ld_as_float(x, (r + 2) * C + c), e = ld_as_float(x, (r + 3) * C + c);
+        s += (a + b) + (d + e);
+      }
+      for (; r < r1; ++r) s += ld_as_float(x, r * C + c);
       atomicAdd(ws + c, s);
     } else {
       const float m = ws[c] * invP;
-      for (int64_t r = r0; r < r1; ++r) {
+      for (; r + 4 <= r1; r += 4) {
+        const float a = ld_as_float(x, r * C + c) - m, b = ld_as_float(x, (r + 1) * C + c) - m,
+                    d = ld_as_float(x, (r + 2) * C + c) - m, e = ld_as_float(x, (r + 3) * C + c) - m;
+        s += (a * a + b * b) + (d * d + e * e);
+      }
+      for (; r < r1; ++r) {
         const float d = ld_as_float(x, r * C + c) - m;
         s = fmaf(d, d, s);
       }
@@ -121,7 +132,20 @@ __global__ void bn_bwd_reduce_kernel(const TX* __restrict__ x, const TG* __restr
   const int q1 = min(HW, q0 + pix_per_block);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a1 = 0.f, a2 = 0.f;
-    for (int q = q0; q < q1; ++q) {
+    int q = q0;
+    for (; q + 4 <= q1; q += 4) {  // 4 independent pixels in flight per thread
+      float xh[4], g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        g[j] = bn_out_grad(x, dy, mean, invstd, gain, bias, gstride, n, (q + j) / W, (q + j) % W, c, H, W, C, relu, up,
+                           xh[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a1 += g[j];
+        a2 = fmaf(g[j], xh[j], a2);
+      }
+    }
+    for (; q < q1; ++q) {
       float xh;
       const float g = bn_out_grad(x, dy, mean, invstd, gain, bias, gstride, n, q / W, q % W, c, H, W, C, relu, up, xh);
       a1 += g;
@@ -340,8 +364,8 @@ extern "C" int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, 
                                     void* stream) {
   ICGAN_REQUIRE(x && ws && mean && invstd && P > 0 && C > 0, "icgan_bn_train_stats: bad arguments");
   ICGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, STREAM));
-  int row_blocks = static_cast<int>((P + 255) / 256);
-  if (row_blocks > 8 * num_sms()) row_blocks = 8 * num_sms();
+  int row_blocks = static_cast<int>((P + 63) / 64);
+  if (row_blocks > 24 * num_sms()) row_blocks = 24 * num_sms();
   const int64_t rpb = (P + row_blocks - 1) / row_blocks;
   row_blocks = static_cast<int>((P + rpb - 1) / rpb);
   const int threads = reduce_threads(C);
@@ -377,7 +401,7 @@ extern "C" int icgan_bn_bwd_reduce(const void* x, const void* dy, const float* m
   ICGAN_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * B * C, STREAM));
   ICGAN_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * B * C, STREAM));
   const int HW = H * W;
-  int slabs = ceil_div(4 * num_sms(), B);
+  int slabs = ceil_div(24 * num_sms(), B);
   if (slabs > (HW + 15) / 16) slabs = (HW + 15) / 16;
   if (slabs < 1) slabs = 1;
   const int ppb = (HW + slabs - 1) / slabs;

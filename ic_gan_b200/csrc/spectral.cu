@@ -21,23 +21,33 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 }
 
 __global__ void sn_zero_kernel(const IcganSnLayer* layers) {
-  if (threadIdx.x < 2) layers[blockIdx.x].scratch[threadIdx.x] = 0.f;
+  const IcganSnLayer L = layers[blockIdx.x];
+  if (threadIdx.x < 2) L.scratch[threadIdx.x] = 0.f;
+  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) L.v[k] = 0.f;
 }
 
-// v_raw[k] = sum_r u[r] W[r][k] ; scratch[0] += |v_raw|^2
+constexpr int kSnRowChunk = 64;
+// v_raw[k] += sum_{r in chunk} u[r] W[r][k]     grid: (col blocks, row chunks, layers)
 __global__ void sn_wt_u_kernel(const IcganSnLayer* layers) {
-  __shared__ float sh[8];
-  const IcganSnLayer L = layers[blockIdx.y];
+  const IcganSnLayer L = layers[blockIdx.z];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= L.cols) return;
+  const int r0 = blockIdx.y * kSnRowChunk;
+  if (k >= L.cols || r0 >= L.rows) return;
+  const int r1 = min(L.rows, r0 + kSnRowChunk);
+  const float* w = L.W + k;
   float acc = 0.f;
-  if (k < L.cols) {
-    const float* w = L.W + k;
-    for (int r = 0; r < L.rows; ++r) acc = fmaf(L.u[r], w[static_cast<int64_t>(r) * L.cols], acc);
-    L.v[k] = acc;
-  }
-  const float s = block_sum(k < L.cols ? acc * acc : 0.f, sh);
-  if (threadIdx.x == 0) atomicAdd(L.scratch, s);
+  for (int r = r0; r < r1; ++r) acc = fmaf(L.u[r], w[static_cast<int64_t>(r) * L.cols], acc);
+  atomicAdd(L.v + k, acc);
+}
+
+// scratch[0] = |v_raw|^2
+__global__ void sn_vnorm_kernel(const IcganSnLayer* layers) {
+  __shared__ float sh[8];
+  const IcganSnLayer L = layers[blockIdx.x];
+  float s = 0.f;
+  for (int k = threadIdx.x; k < L.cols; k += blockDim.x) s = fmaf(L.v[k], L.v[k], s);
+  const float t = block_sum(s, sh);
+  if (threadIdx.x == 0) L.scratch[0] = t;
 }
 
 // t[r] = sum_k W[r][k] v_raw[k] / max(|v_raw|, eps) ; scratch[1] += t[r]^2     (one warp per row)
@@ -140,8 +150,10 @@ using namespace icgan;
 extern "C" int icgan_sn_power_iteration(const IcganSnLayer* layers_dev, int n_layers, int max_rows, int max_cols,
                                         float eps, int update_u, void* stream) {
   ICGAN_REQUIRE(layers_dev && n_layers > 0 && max_rows > 0 && max_cols > 0, "icgan_sn_power_iteration: bad arguments");
-  sn_zero_kernel<<<n_layers, 32, 0, STREAM>>>(layers_dev);
-  sn_wt_u_kernel<<<dim3((max_cols + 127) / 128, n_layers), 128, 0, STREAM>>>(layers_dev);
+  sn_zero_kernel<<<n_layers, 256, 0, STREAM>>>(layers_dev);
+  sn_wt_u_kernel<<<dim3((max_cols + 127) / 128, (max_rows + kSnRowChunk - 1) / kSnRowChunk, n_layers), 128, 0,
+                   STREAM>>>(layers_dev);
+  sn_vnorm_kernel<<<n_layers, 256, 0, STREAM>>>(layers_dev);
   sn_w_v_kernel<<<dim3((max_rows + 7) / 8, n_layers), 256, 0, STREAM>>>(layers_dev, eps);
   sn_finish_kernel<<<n_layers, 256, 0, STREAM>>>(layers_dev, eps, update_u);
   ICGAN_LAUNCH_CHECK();

@@ -159,6 +159,10 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
         _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
                lambda: call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k,
                             dt(y), rdt, res_shift, act, stream_ptr()))
+    elif min(cin, cout) <= 4 and residual is None:
+        w32 = wk if wk.dtype == torch.float32 else wk32
+        call("icgan_conv2d_small", ptr(x), ptr(w32), ptr(bias), ptr(y), B, H, W, cin, cout, k, dt(x), dt(y), act,
+             stream_ptr())
     else:
         w32 = wk if wk.dtype == torch.float32 else wk32
         if w32 is None:
@@ -223,6 +227,9 @@ class SNConvFn(torch.autograd.Function):
                 _timed("tc_wgrad_kernel", 2.0 * B * H * W * cout * cin * k * k,
                        lambda: call("icgan_conv2d_wgrad_tc", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k,
                                     stream_ptr()))
+            elif min(cin, cout) <= 4:
+                call("icgan_conv2d_wgrad_small", ptr(x), ptr(dy), ptr(G), B, H, W, cin, cout, k, dt(x), dt(dy),
+                     stream_ptr())
             else:
                 call("icgan_conv2d_wgrad_simt", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, 1, k // 2, dt(x),
                      stream_ptr())

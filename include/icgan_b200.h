@@ -63,6 +63,12 @@ int icgan_conv2d_simt(const void* x, const float* wk, const float* bias, const v
 /* dwk (float32, accumulated) from NHWC x [B,H,W,Cin] and dy [B,Hout,Wout,Cout] of dtype in_dtype. */
 int icgan_conv2d_wgrad_simt(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin, int Cout,
                             int ksize, int stride, int pad, int in_dtype, void* stream);
+/* Image-side layers where Cin<=4 or Cout<=4 (RGB): HBM-bound streaming kernels instead of GEMM tiles. wk float32
+ * [Cout,k,k,Cin], k in {1,3}, stride 1, pad k/2; serves forward and (with the dgrad weight copy) dgrad. */
+int icgan_conv2d_small(const void* x, const float* wk, const float* bias, void* y, int B, int H, int W, int Cin,
+                       int Cout, int ksize, int in_dtype, int out_dtype, int act, void* stream);
+int icgan_conv2d_wgrad_small(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin, int Cout,
+                             int ksize, int x_dtype, int dy_dtype, void* stream);
 /* out[c] += sum over pixels of x[p][c]  (bias gradient; NHWC column sums). */
 int icgan_channel_sum(const void* x, float* out, int64_t pixels, int C, int dtype, void* stream);
 
