@@ -55,8 +55,9 @@ SIGNATURES = {
     "icgan_unpool2": [vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, i32, vp],
     "icgan_relu_sumpool": [vp, fp, i32, i32, i32, i32, vp],
     "icgan_relu_sumpool_bwd": [vp, fp, vp, i32, i32, i32, i32, vp],
-    "icgan_softmax_rows": [vp, vp, i64, i32, i32, vp],
-    "icgan_softmax_rows_bwd": [vp, vp, vp, i64, i32, i32, vp],
+    "icgan_softmax_rows": [vp, vp, i64, i32, i32, i32, vp],
+    "icgan_softmax_rows_bwd": [vp, vp, vp, i64, i32, i32, i32, i32, vp],
+    "icgan_gemm_tc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
     "icgan_gemm": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, fp, f32, fp, i32,
                    i32, i32, vp],
 }

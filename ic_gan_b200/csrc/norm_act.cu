@@ -320,12 +320,12 @@ __global__ void relu_sumpool_bwd_kernel(const T* __restrict__ x, const float* __
 }
 
 // ---------------------------------------------------------------- softmax over rows (attention maps, layers.py:237)
-template <typename T>
-__global__ void softmax_rows_kernel(const T* __restrict__ s, T* __restrict__ p, int64_t rows, int cols) {
+template <typename TS, typename TP>
+__global__ void softmax_rows_kernel(const TS* __restrict__ s, TP* __restrict__ p, int64_t rows, int cols) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const T* sr = s + row * cols;
+  const TS* sr = s + row * cols;
   float mx = -INFINITY;
   for (int j = lane; j < cols; j += 32) mx = fmaxf(mx, ld_as_float(sr, j));
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -333,22 +333,22 @@ __global__ void softmax_rows_kernel(const T* __restrict__ s, T* __restrict__ p, 
   for (int j = lane; j < cols; j += 32) sum += __expf(ld_as_float(sr, j) - mx);
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = 1.f / sum;
-  T* pr = p + row * cols;
+  TP* pr = p + row * cols;
   for (int j = lane; j < cols; j += 32) st_from_float(pr, j, __expf(ld_as_float(sr, j) - mx) * inv);
 }
 // ds = p * (dp - sum_j dp_j p_j)
-template <typename T>
-__global__ void softmax_rows_bwd_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds,
+template <typename TP, typename TD, typename TO>
+__global__ void softmax_rows_bwd_kernel(const TP* __restrict__ p, const TD* __restrict__ dp, TO* __restrict__ ds,
                                         int64_t rows, int cols) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const T* pr = p + row * cols;
-  const T* dr = dp + row * cols;
+  const TP* pr = p + row * cols;
+  const TD* dr = dp + row * cols;
   float dot = 0.f;
   for (int j = lane; j < cols; j += 32) dot = fmaf(ld_as_float(pr, j), ld_as_float(dr, j), dot);
   for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  T* or_ = ds + row * cols;
+  TO* or_ = ds + row * cols;
   for (int j = lane; j < cols; j += 32) st_from_float(or_, j, ld_as_float(pr, j) * (ld_as_float(dr, j) - dot));
 }
 
@@ -530,23 +530,25 @@ extern "C" int icgan_relu_sumpool_bwd(const void* x, const float* dh, void* dx, 
   return 0;
 }
 
-extern "C" int icgan_softmax_rows(const void* s, void* p, int64_t rows, int cols, int dtype, void* stream) {
+extern "C" int icgan_softmax_rows(const void* s, void* p, int64_t rows, int cols, int s_dtype, int p_dtype,
+                                  void* stream) {
   ICGAN_REQUIRE(s && p && rows > 0 && cols > 0, "icgan_softmax_rows: bad arguments");
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-  DISPATCH_T(dtype, T, {
-    softmax_rows_kernel<T><<<blocks, 256, 0, STREAM>>>(static_cast<const T*>(s), static_cast<T*>(p), rows, cols);
-  })
+  DISPATCH_T(s_dtype, TS, {DISPATCH_T(p_dtype, TP, {
+    softmax_rows_kernel<TS, TP><<<blocks, 256, 0, STREAM>>>(static_cast<const TS*>(s), static_cast<TP*>(p), rows, cols);
+  })})
   ICGAN_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int icgan_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, int cols, int dtype,
-                                      void* stream) {
+extern "C" int icgan_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, int cols, int p_dtype,
+                                      int dp_dtype, int ds_dtype, void* stream) {
   ICGAN_REQUIRE(p && dp && ds && rows > 0 && cols > 0, "icgan_softmax_rows_bwd: bad arguments");
+  ICGAN_REQUIRE(dp != ds || dp_dtype == ds_dtype, "icgan_softmax_rows_bwd: in-place needs equal dtypes");
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-  DISPATCH_T(dtype, T, {
-    softmax_rows_bwd_kernel<T><<<blocks, 256, 0, STREAM>>>(static_cast<const T*>(p), static_cast<const T*>(dp),
-                                                          static_cast<T*>(ds), rows, cols);
-  })
+  DISPATCH_T(p_dtype, TP, {DISPATCH_T(dp_dtype, TD, {DISPATCH_T(ds_dtype, TO, {
+    softmax_rows_bwd_kernel<TP, TD, TO><<<blocks, 256, 0, STREAM>>>(
+        static_cast<const TP*>(p), static_cast<const TD*>(dp), static_cast<TO*>(ds), rows, cols);
+  })})})
   ICGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -457,22 +457,37 @@ class ScaleAddFn(torch.autograd.Function):
         return do, dy, dgamma
 
 
+def _gemm_tc(A, B_, Cm, M, N, K, batch, a_mn, b_mn, lda, sab, ldb, sbb, ldc, scb, alpha=1.0):
+    _timed("tc_gemm_kernel", 2.0 * batch * M * N * K,
+           lambda: call("icgan_gemm_tc", ptr(A), ptr(B_), ptr(Cm), M, N, K, batch, int(a_mn), int(b_mn), lda, sab, ldb,
+                        sbb, ldc, scb, float(alpha), dt(Cm), stream_ptr()))
+
+
 class AttentionCoreFn(torch.autograd.Function):
     """o[b,q,:] = sum_k softmax_k(theta[b,q,:] . phi[b,k,:]) * g[b,k,:]   (layers.py:233-243) on NHWC-flattened
-    theta [B,Q,d], pooled phi [B,Kk,d], pooled g [B,Kk,dv]."""
+    theta [B,Q,d], pooled phi [B,Kk,d], pooled g [B,Kk,dv].  bfloat16 inputs run on the batched tcgen05 GEMM (logits and
+    their gradient kept in float32, probabilities in bf16); float32 inputs on the CUDA-core GEMM."""
 
     @staticmethod
     def forward(ctx, theta, phi, g):
         theta, phi, g = theta.contiguous(), phi.contiguous(), g.contiguous()
         B, Q, d = theta.shape
         Kk, dv = phi.shape[1], g.shape[2]
-        S = torch.empty(B, Q, Kk, device=theta.device, dtype=theta.dtype)
-        _gemm(theta, phi, S, Q, Kk, d, (d, 1), (1, d), (Kk, 1), batch=B, bstrides=(Q * d, Kk * d, Q * Kk))
-        P = torch.empty_like(S)
-        call("icgan_softmax_rows", ptr(S), ptr(P), B * Q, Kk, dt(S), stream_ptr())
+        tc = theta.dtype == torch.bfloat16 and d % 8 == 0 and dv % 8 == 0 and Kk % 8 == 0
+        S = torch.empty(B, Q, Kk, device=theta.device, dtype=torch.float32)
+        if tc:
+            _gemm_tc(theta, phi, S, Q, Kk, d, B, 0, 0, d, Q * d, d, Kk * d, Kk, Q * Kk)
+        else:
+            _gemm(theta, phi, S, Q, Kk, d, (d, 1), (1, d), (Kk, 1), batch=B, bstrides=(Q * d, Kk * d, Q * Kk))
+        P = torch.empty(B, Q, Kk, device=theta.device, dtype=theta.dtype)
+        call("icgan_softmax_rows", ptr(S), ptr(P), B * Q, Kk, dt(S), dt(P), stream_ptr())
         del S
         o = torch.empty(B, Q, dv, device=theta.device, dtype=theta.dtype)
-        _gemm(P, g, o, Q, dv, Kk, (Kk, 1), (dv, 1), (dv, 1), batch=B, bstrides=(Q * Kk, Kk * dv, Q * dv))
+        if tc:
+            _gemm_tc(P, g, o, Q, dv, Kk, B, 0, 1, Kk, Q * Kk, dv, Kk * dv, dv, Q * dv)
+        else:
+            _gemm(P, g, o, Q, dv, Kk, (Kk, 1), (dv, 1), (dv, 1), batch=B, bstrides=(Q * Kk, Kk * dv, Q * dv))
+        ctx.tc = tc
         ctx.save_for_backward(theta, phi, g, P)
         return o
 
@@ -482,14 +497,24 @@ class AttentionCoreFn(torch.autograd.Function):
         do = do.contiguous()
         B, Q, d = theta.shape
         Kk, dv = phi.shape[1], g.shape[2]
-        dP = torch.empty_like(P)
-        _gemm(do, g, dP, Q, Kk, dv, (dv, 1), (1, dv), (Kk, 1), batch=B, bstrides=(Q * dv, Kk * dv, Q * Kk))
+        tc = ctx.tc
+        dP = torch.empty(B, Q, Kk, device=P.device, dtype=torch.float32)
         dg = torch.empty_like(g)
-        _gemm(P, do, dg, Kk, dv, Q, (1, Kk), (dv, 1), (dv, 1), batch=B, bstrides=(Q * Kk, Q * dv, Kk * dv))
-        dS = dP
-        call("icgan_softmax_rows_bwd", ptr(P), ptr(dP), ptr(dS), B * Q, Kk, dt(P), stream_ptr())
+        if tc:
+            _gemm_tc(do, g, dP, Q, Kk, dv, B, 0, 0, dv, Q * dv, dv, Kk * dv, Kk, Q * Kk)
+            _gemm_tc(P, do, dg, Kk, dv, Q, B, 1, 1, Kk, Q * Kk, dv, Q * dv, dv, Kk * dv)
+        else:
+            _gemm(do, g, dP, Q, Kk, dv, (dv, 1), (1, dv), (Kk, 1), batch=B, bstrides=(Q * dv, Kk * dv, Q * Kk))
+            _gemm(P, do, dg, Kk, dv, Q, (1, Kk), (dv, 1), (dv, 1), batch=B, bstrides=(Q * Kk, Q * dv, Kk * dv))
+        dS = dP if P.dtype == torch.float32 else torch.empty_like(P)
+        call("icgan_softmax_rows_bwd", ptr(P), ptr(dP), ptr(dS), B * Q, Kk, dt(P), dt(dP), dt(dS), stream_ptr())
         dtheta = torch.empty_like(theta)
-        _gemm(dS, phi, dtheta, Q, d, Kk, (Kk, 1), (d, 1), (d, 1), batch=B, bstrides=(Q * Kk, Kk * d, Q * d))
         dphi = torch.empty_like(phi)
-        _gemm(dS, theta, dphi, Kk, d, Q, (1, Kk), (d, 1), (d, 1), batch=B, bstrides=(Q * Kk, Q * d, Kk * d))
+        if tc:
+            del dP
+            _gemm_tc(dS, phi, dtheta, Q, d, Kk, B, 0, 1, Kk, Q * Kk, d, Kk * d, d, Q * d)
+            _gemm_tc(dS, theta, dphi, Kk, d, Q, B, 1, 1, Kk, Q * Kk, d, Q * d, d, Kk * d)
+        else:
+            _gemm(dS, phi, dtheta, Q, d, Kk, (Kk, 1), (d, 1), (d, 1), batch=B, bstrides=(Q * Kk, Kk * d, Q * d))
+            _gemm(dS, theta, dphi, Kk, d, Q, (1, Kk), (d, 1), (d, 1), batch=B, bstrides=(Q * Kk, Q * d, Kk * d))
         return dtheta, dphi, dg

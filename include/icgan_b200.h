@@ -141,8 +141,9 @@ int icgan_unpool2(const void* dy, const void* xref, void* dx, int B, int Hout, i
                   int ref_dtype, int g_dtype, void* stream);
 int icgan_relu_sumpool(const void* x, float* out, int B, int HW, int C, int dtype, void* stream);
 int icgan_relu_sumpool_bwd(const void* x, const float* dh, void* dx, int B, int HW, int C, int dtype, void* stream);
-int icgan_softmax_rows(const void* s, void* p, int64_t rows, int cols, int dtype, void* stream);
-int icgan_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, int cols, int dtype, void* stream);
+int icgan_softmax_rows(const void* s, void* p, int64_t rows, int cols, int s_dtype, int p_dtype, void* stream);
+int icgan_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t rows, int cols, int p_dtype, int dp_dtype,
+                           int ds_dtype, void* stream);
 
 /* Strided batched GEMM on CUDA cores, float32 accumulate (SNLinear layers.py:164-165; attention bmm layers.py:237-243):
  * C[b][m][n] = alpha*(alpha_dev?*alpha_dev:1) * sum_k A[b][m][k]*B[b][k][n] + bias[n] + beta*C[b][m][n]; strides in elements. */
@@ -150,6 +151,14 @@ int icgan_gemm(const void* A, const void* B, void* C, int M, int N, int K, int b
                int64_t sab, int64_t sbk, int64_t sbn, int64_t sbb, int64_t scm, int64_t scn, int64_t scb, float alpha,
                const float* alpha_dev, float beta, const float* bias, int a_dtype, int b_dtype, int c_dtype,
                void* stream);
+
+/* Batched tensor-core GEMM (tcgen05, bf16 operands, fp32 accumulate) for the attention products torch.bmm computes in
+ * layers.Attention.forward (layers.py:237-243) and their backward: C[b] = alpha * op(A[b]) op(B[b]), C [M,N] row-major
+ * (ldc), dtype c_dtype. a_mn/b_mn = 0: operand stored [rows][K] (K contiguous, ld = row stride); = 1: stored [K][rows]
+ * (rows contiguous, ld = stride between K indices). sab/sbb/scb: batch strides (elements). ld*, N multiples of 8. */
+int icgan_gemm_tc(const void* A, const void* B, void* C, int M, int N, int K, int batch, int a_mn, int b_mn, int64_t lda,
+                  int64_t sab, int64_t ldb, int64_t sbb, int64_t ldc, int64_t scb, float alpha, int c_dtype,
+                  void* stream);
 
 #ifdef __cplusplus
 }
