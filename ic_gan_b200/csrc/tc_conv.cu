@@ -111,7 +111,8 @@ struct TcConvParams {
   int TW, TH, TN;
   int tiles_w, tiles_h, n_tiles, total_tiles;
   int BN, cw, chunks, k_iters, stages;
-  uint32_t a_bytes, b_tx, stage_bytes, swz, idesc;
+  int G, n_stage_iters;            // k-chunks per pipeline stage, stage iterations per tile
+  uint32_t a_bytes, b_tx, b_chunk, stage_bytes, swz, idesc;
   int out_bf16, res_bf16, res_shift, act;
   void* y;
   const float* bias;
@@ -171,26 +172,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // One pipeline stage carries up to G k-chunks (G A-boxes + G B-boxes, one barrier round trip), so that the MMA
+    // thread always has >= ~4 UMMAs per wait. Tap/chunk counters advance incrementally: no integer division here.
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t chunk_tx = p.a_bytes + p.b_tx;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dh = tap / p.ksz - p.pad, dw = tap % p.ksz - p.pad;
-          for (int cc = 0; cc < p.chunks; ++cc) {
-            mbar_wait(&empty[stage], phase ^ 1u);
-            uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
-            uint8_t* sb = sa + p.a_bytes;
-            mbar_expect_tx(&full[stage], p.a_bytes + p.b_tx);
+        int tap = 0, cc = 0, dh = -p.pad, dw = -p.pad, left = p.k_iters;
+        for (int it = 0; it < p.n_stage_iters; ++it) {
+          const int n = left < p.G ? left : p.G;
+          left -= n;
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
+          uint8_t* sb = sa + static_cast<size_t>(p.G) * p.a_bytes;
+          mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * chunk_tx);
+          for (int g = 0; g < n; ++g) {
             tma_load_4d(sa, &tmA, &full[stage], cc * p.cw, t.w0 + dw, t.h0 + dh, t.n0);
             tma_load_3d(sb, &tmB, &full[stage], cc * p.cw, tap, t.co0);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
+            sa += p.a_bytes;
+            sb += p.b_chunk;
+            if (++cc == p.chunks) {
+              cc = 0;
+              ++tap;
+              if (++dw > p.pad) {
+                dw = -p.pad;
+                ++dh;
+              }
             }
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -201,18 +217,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const int ksteps = p.cw / 16;
+      const uint64_t desc0 = umma_desc_kmajor(0, p.swz);  // everything but the start address
+      const uint32_t a_step = p.a_bytes >> 4, b_step = p.b_chunk >> 4;
+      const uint32_t b_off = (static_cast<uint32_t>(p.G) * p.a_bytes) >> 4;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
-        for (int it = 0; it < p.k_iters; ++it) {
+        int left = p.k_iters;
+        uint32_t first = 0;  // 0 for the very first UMMA of the tile (overwrite), 1 afterwards (accumulate)
+        for (int it = 0; it < p.n_stage_iters; ++it) {
+          const int n = left < p.G ? left : p.G;
+          left -= n;
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = base + static_cast<uint32_t>(stage) * p.stage_bytes;
-          const uint64_t da = umma_desc_kmajor(sa, p.swz);
-          const uint64_t db = umma_desc_kmajor(sa + p.a_bytes, p.swz);
-          for (int k = 0; k < ksteps; ++k)  // +32 bytes (16 bf16) along K inside the swizzle atom
-            umma_bf16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+          uint64_t da = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
+          uint64_t db = da + b_off;
+          for (int g = 0; g < n; ++g) {
+            for (int k = 0; k < ksteps; ++k) {  // +32 bytes (16 bf16) along K inside the swizzle atom
+              umma_bf16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, first);
+              first = 1u;
+            }
+            da += a_step;
+            db += b_step;
+          }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) {
             stage = 0;
@@ -290,20 +318,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------ wgrad
 // dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci], operands read straight from the NHWC tensors:
 // the reduction index (pixels) is the ROW of each TMA box and channels are contiguous, i.e. both UMMA operands are
-// "MN-major".  A stage holds KP=32 pixels: A = two 64-channel boxes of dY (M = 128 output channels),
-// B = for every filter tap one or more 64-channel boxes of X at the tap-shifted pixel coordinates (halo zero-filled
-// by TMA).  All taps accumulate concurrently into TMEM (tap t at columns [t*CT, (t+1)*CT)), so dY is read once.
+// "MN-major".  A stage holds KP=64 pixels: A = two 64-channel boxes of dY (M = 128 output channels); B = one
+// 64-channel box of X per filter tap at the tap-shifted pixel coordinates (halo zero-filled by TMA).  The tap boxes sit
+// back to back in shared memory, so they are simply consecutive 64-wide COLUMN GROUPS of one MN-major B operand
+// (leading-dimension byte offset = box size): a single UMMA with N=256 multiplies dY against 4 taps at once.
+// A CTA owns a group of <= 5 taps (5*64 = 320 of the 512 TMEM columns); 3x3 filters use two groups (5 + 4 taps).
+// For 1x1 filters the column groups are further input channels instead of taps.
 struct TcWgradParams {
   int Cin, Cout, ksz, pad, taps;
   int TW, TH, TN;
   int tiles_w, tiles_h, tiles_b, k_chunks;
-  int co_tiles, ci_tiles, splits;
-  int CT, b_boxes, stages;
-  uint32_t a_bytes, box_bytes, stage_bytes, idesc;
+  int co_tiles, ci_tiles, groups, splits;
+  int ci_per_tile, stages;
+  uint32_t a_bytes, box_bytes, stage_bytes;
   float* dwk;
 };
 
-static constexpr int kWgradKP = 32;  // pixels (reduction rows) per pipeline stage
+static constexpr int kWgradKP = 64;      // pixels (reduction rows) per pipeline stage
+static constexpr int kWgradMaxBoxes = 5;  // 64-channel column groups per CTA
 
 // MN-major SW128 operand: 64-channel column groups `lbo_bytes` apart, 8-pixel row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -346,17 +378,30 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work item: (co tile, ci tile, pixel-chunk range)
+  // work item: (co tile, tap/channel group, ci tile, pixel-chunk range)
   int wi = blockIdx.x;
   const int split = wi % p.splits;
   wi /= p.splits;
   const int ci_t = wi % p.ci_tiles;
-  const int co_t = wi / p.ci_tiles;
+  wi /= p.ci_tiles;
+  const int grp = wi % p.groups;
+  const int co_t = wi / p.groups;
   const int per = (p.k_chunks + p.splits - 1) / p.splits;
   const int kc_begin = split * per;
   const int kc_end = min(p.k_chunks, kc_begin + per);
   const int n_chunks = max(0, kc_end - kc_begin);
-  const int co0 = co_t * 128, ci0 = ci_t * p.CT;
+  const int co0 = co_t * 128, ci0 = ci_t * p.ci_per_tile;
+  // column groups (boxes) of this CTA: taps [tap0, tap0+nb) for 3x3, further 64-channel slices for 1x1
+  int tap0 = 0, nb;
+  if (p.taps > 1) {
+    tap0 = grp * kWgradMaxBoxes;
+    nb = min(kWgradMaxBoxes, p.taps - tap0);
+  } else {
+    nb = min(kWgradMaxBoxes, (min(p.ci_per_tile, p.Cin - ci0) + 63) / 64);
+  }
+  const uint32_t n1 = static_cast<uint32_t>(min(nb, 4) * 64), n2 = static_cast<uint32_t>((nb - min(nb, 4)) * 64);
+  const uint32_t idesc1 = umma_idesc_bf16(128, n1) | (1u << 15) | (1u << 16);  // A and B MN-major
+  const uint32_t idesc2 = umma_idesc_bf16(128, n2 ? n2 : 64) | (1u << 15) | (1u << 16);
 
   if (warp == 0) {
     if (lane == 0 && n_chunks > 0) {
@@ -364,23 +409,37 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
       tma_prefetch_desc(&tmX);
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t tx = p.a_bytes + static_cast<uint32_t>(nb) * p.box_bytes;
+      int tw = kc_begin % p.tiles_w, th = (kc_begin / p.tiles_w) % p.tiles_h, tb = kc_begin / (p.tiles_w * p.tiles_h);
+      const int dh0 = p.taps > 1 ? tap0 / p.ksz - p.pad : 0, dw0 = p.taps > 1 ? tap0 % p.ksz - p.pad : 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
-        int t = kc;
-        const int tw = t % p.tiles_w;
-        t /= p.tiles_w;
-        const int th = t % p.tiles_h;
-        const int tb = t / p.tiles_h;
         const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tb * p.TN;
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            ++tb;
+          }
+        }
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
-        mbar_expect_tx(&full[stage], p.a_bytes + static_cast<uint32_t>(p.taps * p.b_boxes) * p.box_bytes);
+        mbar_expect_tx(&full[stage], tx);
         tma_load_4d(sa, &tmDy, &full[stage], co0, w0, h0, n0);
         tma_load_4d(sa + p.box_bytes, &tmDy, &full[stage], co0 + 64, w0, h0, n0);
         uint8_t* sb = sa + p.a_bytes;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dh = tap / p.ksz - p.pad, dw = tap % p.ksz - p.pad;
-          for (int bx = 0; bx < p.b_boxes; ++bx) {
-            tma_load_4d(sb, &tmX, &full[stage], ci0 + bx * 64, w0 + dw, h0 + dh, n0);
+        if (p.taps > 1) {
+          int dh = dh0, dw = dw0;
+          for (int j = 0; j < nb; ++j) {
+            tma_load_4d(sb, &tmX, &full[stage], ci0, w0 + dw, h0 + dh, n0);
+            sb += p.box_bytes;
+            if (++dw > p.pad) {
+              dw = -p.pad;
+              ++dh;
+            }
+          }
+        } else {
+          for (int j = 0; j < nb; ++j) {
+            tma_load_4d(sb, &tmX, &full[stage], ci0 + 64 * j, w0, h0, n0);
             sb += p.box_bytes;
           }
         }
@@ -394,18 +453,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
     if (lane == 0 && n_chunks > 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t desc0 = umma_desc_mnmajor(0, p.box_bytes);
+      const uint32_t b_off = p.a_bytes >> 4, b2_off = (p.a_bytes + 4u * p.box_bytes) >> 4;
       for (int it = 0; it < n_chunks; ++it) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sa = base + static_cast<uint32_t>(stage) * p.stage_bytes;
-        const uint64_t da = umma_desc_mnmajor(sa, p.box_bytes);
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const uint64_t db =
-              umma_desc_mnmajor(sa + p.a_bytes + static_cast<uint32_t>(tap * p.b_boxes) * p.box_bytes, p.box_bytes);
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(tap * p.CT);
+        const uint64_t da = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
-          for (int k = 0; k < kWgradKP / 16; ++k)  // 16 pixel rows = 2 swizzle atoms = 2048 bytes per UMMA
-            umma_bf16(d_tmem, da + 128u * k, db + 128u * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kWgradKP / 16; ++k) {  // 16 pixel rows = 2 swizzle atoms = 2048 bytes per UMMA
+          const uint32_t accf = (it | k) != 0 ? 1u : 0u;
+          umma_bf16(tmem_base, da + 128u * k, da + b_off + 128u * k, idesc1, accf);
+          if (n2) umma_bf16(tmem_base + 256u, da + 128u * k, da + b2_off + 128u * k, idesc2, accf);
         }
         umma_commit(&empty[stage]);
         if (++stage == p.stages) {
@@ -421,16 +479,18 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
     mbar_wait(&tfull[0], 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int tap = 0; tap < p.taps; ++tap) {
-      for (int c = 0; c < p.CT; c += 16) {
+    for (int j = 0; j < nb; ++j) {
+      const int tap = p.taps > 1 ? tap0 + j : 0;
+      const int cib = p.taps > 1 ? ci0 : ci0 + 64 * j;
+      for (int c = 0; c < 64; c += 16) {
         uint32_t r[16];
-        tmem_ld16(taddr + static_cast<uint32_t>(tap * p.CT + c), r);
+        tmem_ld16(taddr + static_cast<uint32_t>(j * 64 + c), r);
         tmem_ld_wait();
         if (co < p.Cout) {
-          float* dst = p.dwk + (static_cast<int64_t>(co) * p.taps + tap) * p.Cin + ci0 + c;
+          float* dst = p.dwk + (static_cast<int64_t>(co) * p.taps + tap) * p.Cin + cib + c;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (ci0 + c + j < p.Cin) atomicAdd(dst + j, __uint_as_float(r[j]));
+          for (int i = 0; i < 16; ++i)
+            if (cib + c + i < p.Cin) atomicAdd(dst + i, __uint_as_float(r[i]));
         }
       }
     }
@@ -495,7 +555,15 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* bias,
   p.total_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
   p.a_bytes = 128u * p.swz;
   p.b_tx = static_cast<uint32_t>(p.BN) * p.swz;
-  p.stage_bytes = p.a_bytes + ((p.b_tx + 1023u) & ~1023u);
+  p.b_chunk = (p.b_tx + 1023u) & ~1023u;
+  const uint32_t chunk_bytes = p.a_bytes + p.b_chunk;
+  int G = static_cast<int>(49152u / chunk_bytes);  // aim at ~48 KB and >= 4 UMMAs per barrier round trip
+  if (G < 1) G = 1;
+  if (G > 8) G = 8;
+  if (G > p.k_iters) G = p.k_iters;
+  p.G = G;
+  p.n_stage_iters = (p.k_iters + G - 1) / G;
+  p.stage_bytes = static_cast<uint32_t>(G) * chunk_bytes;
   const uint32_t tail = 1024u /*align slack*/ + 512u /*barriers*/;
   int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -551,24 +619,24 @@ extern "C" int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, 
   p.tiles_h = ceil_div(H, p.TH);
   p.tiles_b = ceil_div(B, p.TN);
   p.k_chunks = p.tiles_w * p.tiles_h * p.tiles_b;
-  if (p.taps == 1) {
-    p.CT = Cin >= 256 ? 256 : (Cin + 15) / 16 * 16;
-  } else {  // all 9 tap accumulators share the 512 TMEM columns and each tap gets one 64-channel box
-    p.CT = (Cin % 48 == 0) ? 48 : (Cin % 32 == 0 ? 32 : 16);
+  if (p.taps > 1) {
+    p.ci_per_tile = 64;
+    p.groups = ceil_div(p.taps, kWgradMaxBoxes);
+  } else {
+    p.ci_per_tile = 64 * kWgradMaxBoxes;
+    p.groups = 1;
   }
-  p.b_boxes = (p.CT + 63) / 64;
   p.co_tiles = ceil_div(Cout, 128);
-  p.ci_tiles = ceil_div(Cin, p.CT);
+  p.ci_tiles = ceil_div(Cin, p.ci_per_tile);
   p.box_bytes = static_cast<uint32_t>(kWgradKP) * 128u;
   p.a_bytes = 2u * p.box_bytes;
-  p.stage_bytes = p.a_bytes + static_cast<uint32_t>(p.taps * p.b_boxes) * p.box_bytes;
+  p.stage_bytes = p.a_bytes + static_cast<uint32_t>(kWgradMaxBoxes) * p.box_bytes;
   const uint32_t tail = 1024u + 512u;
   int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
   if (stages > 8) stages = 8;
   ICGAN_REQUIRE(stages >= 2, "icgan_conv2d_wgrad_tc: tile does not fit shared memory");
   p.stages = stages;
-  p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.CT)) | (1u << 15) | (1u << 16);  // A and B MN-major
-  const int out_tiles = p.co_tiles * p.ci_tiles;
+  const int out_tiles = p.co_tiles * p.ci_tiles * p.groups;
   int splits = ceil_div(2 * num_sms(), out_tiles);
   if (splits > p.k_chunks) splits = p.k_chunks;
   if (splits < 1) splits = 1;

@@ -216,9 +216,32 @@ static int run_wgrad_case(const WgradCase& c, bool time_it) {
   return bad ? 1 : 0;
 }
 
+// launches only (no host reference): target for `ncu --set full`
+static void run_prof() {
+  const int B = 32, H = 64, W = 64, Ci = 384, Co = 384, k = 3;
+  const size_t nx = (size_t)B * H * W * Ci, ny = (size_t)B * H * W * Co, nw = (size_t)Co * 9 * Ci;
+  void *x, *y, *w;
+  float* dw;
+  CK(cudaMalloc(&x, nx * 2)); CK(cudaMalloc(&y, ny * 2)); CK(cudaMalloc(&w, nw * 2)); CK(cudaMalloc(&dw, nw * 4));
+  CK(cudaMemset(x, 0x3c, nx * 2)); CK(cudaMemset(y, 0x3c, ny * 2)); CK(cudaMemset(w, 0x3c, nw * 2));
+  CK(cudaMemset(dw, 0, nw * 4));
+  for (int i = 0; i < 3; ++i) {
+    icgan_conv2d_tc(x, w, nullptr, nullptr, y, B, H, W, Ci, Co, k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
+    icgan_conv2d_wgrad_tc(x, y, dw, B, H, W, Ci, Co, k, nullptr);
+  }
+  // the 96-channel 256x256 layer (HBM/overhead-bound regime)
+  for (int i = 0; i < 2; ++i) {
+    icgan_conv2d_tc(x, w, nullptr, nullptr, y, 8, 256, 256, 96, 96, k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
+    icgan_conv2d_wgrad_tc(x, y, dw, 8, 256, 256, 96, 96, k, nullptr);
+  }
+  CK(cudaDeviceSynchronize());
+  printf("prof launches done\n");
+}
+
 int main(int argc, char** argv) {
-  // usage: tc_selftest [all|conv|wgrad <idx>|perf]
+  // usage: tc_selftest [all|conv|wgrad <idx>|perf|prof]
   const char* mode = argc > 1 ? argv[1] : "all";
+  if (!strcmp(mode, "prof")) { run_prof(); return 0; }
   const bool perf = !strcmp(mode, "perf");
   const bool do_conv = !strcmp(mode, "all") || !strcmp(mode, "conv") || perf;
   const bool do_wgrad = !strcmp(mode, "all") || !strcmp(mode, "wgrad") || perf;
