@@ -57,6 +57,10 @@ SIGNATURES = {
     "icgan_relu_sumpool_bwd": [vp, fp, vp, i32, i32, i32, i32, vp],
     "icgan_softmax_rows": [vp, vp, i64, i32, i32, i32, vp],
     "icgan_softmax_rows_bwd": [vp, vp, vp, i64, i32, i32, i32, i32, vp],
+    "icgan_knn_prepare": [fp, vp, vp, fp, i64, i32, vp],
+    "icgan_knn_coarse": [vp, vp, fp, i64, i32, i64, i64, i32, i32, vp, fp, vp],
+    "icgan_knn_rerank": [fp, i64, i32, i64, i64, i32, i32, vp, fp, vp, vp, vp, fp, f32, vp],
+    "icgan_knn_exact_row": [fp, i64, i32, i64, i32, vp, vp, vp, vp],
     "icgan_gemm_tc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
     "icgan_gemm": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, fp, f32, fp, i32,
                    i32, i32, vp],
@@ -88,7 +92,7 @@ def last_error() -> str:
 
 
 # kernels launched per entry point (everything else launches exactly one); bench.py reports the running total
-KERNELS_PER_CALL = {"icgan_bn_train_stats": 3, "icgan_sn_power_iteration": 5, "icgan_sn_weight_grad": 2}
+KERNELS_PER_CALL = {"icgan_bn_train_stats": 3, "icgan_sn_power_iteration": 5, "icgan_sn_weight_grad": 2, "icgan_knn_exact_row": 2}
 LAUNCHES = 0
 
 

@@ -160,6 +160,27 @@ int icgan_gemm_tc(const void* A, const void* B, void* C, int M, int N, int K, in
                   int64_t sab, int64_t ldb, int64_t sbb, int64_t ldc, int64_t scb, float alpha, int c_dtype,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * k-NN conditioning build (replaces faiss.IndexFlatL2.add/search in ILSVRC_HDF5_feats._obtain_nns,
+ * data_utils/datasets_common.py:695-745; output format of data_utils/make_hdf5_nns.py:132-172).
+ * X: [N, d] float32 row-major (the float32 cast of the float64-normalised features, datasets_common.py:422-428).
+ * ---------------------------------------------------------------------------------------------- */
+/* split-bf16 copies (hi, lo) of X and squared norms; Xhi/Xlo: [N, d] bf16, norms: [N] float32. */
+int icgan_knn_prepare(const float* X, void* Xhi, void* Xlo, float* norms, int64_t N, int d, void* stream);
+/* Tensor-core distance sweep for query rows [q_begin, q_end): per row the C (<=64) smallest coarse squared distances
+ * (ascending) and their database indices. passes = 3 (hi.hi+hi.lo+lo.hi, ~fp32 accuracy) or 1 (bf16). d %% 8 == 0. */
+int icgan_knn_coarse(const void* Xhi, const void* Xlo, const float* norms, int64_t N, int d, int64_t q_begin,
+                     int64_t q_end, int C, int passes, int* cand_idx, float* cand_d, void* stream);
+/* Exact float64 re-rank of the candidates: nn_out [nq, k] int64 (self removed by value, ties -> lower index),
+ * radius_out [nq] (float32 sqrt of the (k+1)-th squared distance, stored as double), flags[nq] = 1 where the row could
+ * not be certified (use icgan_knn_exact_row), *max_err = max |coarse - exact| seen (float, device). */
+int icgan_knn_rerank(const float* X, int64_t N, int d, int64_t q_begin, int64_t q_end, int C, int k,
+                     const int* cand_idx, const float* cand_d, int64_t* nn_out, double* radius_out, int* flags,
+                     float* max_err, float margin, void* stream);
+/* Brute-force float64 answer for one row (scratch: N doubles). */
+int icgan_knn_exact_row(const float* X, int64_t N, int d, int64_t row, int k, double* scratch, int64_t* nn_out_row,
+                        double* radius_out_row, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
