@@ -3,6 +3,7 @@
 // wgrad, strided StyleGAN2 convs).  Reference: F.conv2d behind layers.SNConv2d.forward (BigGAN_PyTorch/layers.py:144-153)
 // and conv2d_gradfix (stylegan2_ada_pytorch/torch_utils/ops/conv2d_gradfix.py:126-272).
 #include "common.cuh"
+#include "norm_act_vec.cuh"
 
 namespace icgan {
 
@@ -264,6 +265,16 @@ extern "C" int icgan_conv2d_wgrad_simt(const void* x, const void* dy, float* dwk
 
 extern "C" int icgan_channel_sum(const void* x, float* out, int64_t P, int C, int dtype, void* stream) {
   ICGAN_REQUIRE(x && out && P > 0 && C > 0, "icgan_channel_sum: bad arguments");
+  if (dtype == ICGAN_BF16 && vec::ok(C)) {
+    int64_t blocks = static_cast<int64_t>(num_sms()) * 8;
+    if (blocks > (P + 127) / 128) blocks = (P + 127) / 128;
+    const int64_t ppb = (P + blocks - 1) / blocks;
+    blocks = (P + ppb - 1) / ppb;
+    vec::colsum_vec_kernel<0><<<static_cast<unsigned>(blocks), vec::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const vec::bf16*>(x), out, P, C, ppb);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   int row_blocks = static_cast<int>((P + 63) / 64);
   if (row_blocks > 24 * num_sms()) row_blocks = 24 * num_sms();
   const int64_t rpb = (P + row_blocks - 1) / row_blocks;

@@ -4,6 +4,7 @@
 // D's global sum pooling (BigGAN.py:624), tanh backward and small elementwise helpers.
 // All index arithmetic is on the flat [pixels][C] view, threads run along C => fully coalesced.
 #include "common.cuh"
+#include "norm_act_vec.cuh"
 
 namespace icgan {
 
@@ -364,6 +365,19 @@ extern "C" int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, 
                                     void* stream) {
   ICGAN_REQUIRE(x && ws && mean && invstd && P > 0 && C > 0, "icgan_bn_train_stats: bad arguments");
   ICGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, STREAM));
+  if (dtype == ICGAN_BF16 && vec::ok(C)) {
+    int64_t blocks = static_cast<int64_t>(num_sms()) * 8;
+    if (blocks > (P + 127) / 128) blocks = (P + 127) / 128;
+    const int64_t ppb = (P + blocks - 1) / blocks;
+    blocks = (P + ppb - 1) / ppb;
+    const vec::bf16* xb = static_cast<const vec::bf16*>(x);
+    vec::colsum_vec_kernel<1><<<static_cast<unsigned>(blocks), vec::kThreads, 0, STREAM>>>(xb, ws, P, C, ppb);
+    vec::colsum_vec_kernel<2><<<static_cast<unsigned>(blocks), vec::kThreads, 0, STREAM>>>(xb, ws, P, C, ppb);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(ws, running_mean, running_var, mean, invstd, P, C, eps,
+                                                            momentum);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   int row_blocks = static_cast<int>((P + 63) / 64);
   if (row_blocks > 24 * num_sms()) row_blocks = 24 * num_sms();
   const int64_t rpb = (P + row_blocks - 1) / row_blocks;
@@ -385,6 +399,13 @@ extern "C" int icgan_bn_apply(const void* x, void* y, const float* mean, const f
                               int in_dtype, int out_dtype, void* stream) {
   ICGAN_REQUIRE(x && y && mean && invstd && gain && bias, "icgan_bn_apply: null pointer");
   const int64_t total = static_cast<int64_t>(B) * H * W * C;
+  if (in_dtype == ICGAN_BF16 && out_dtype == ICGAN_BF16 && vec::ok(C)) {
+    vec::bn_apply_vec_kernel<<<vec::blocks_for(total / 8), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(x), static_cast<vec::bf16*>(y), mean, invstd, gain, bias, gain_stride, B, H, W, C,
+        relu, up);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = ew_blocks(total);
   DISPATCH_T(in_dtype, TI, {DISPATCH_T(out_dtype, TO, {
     bn_apply_kernel<TI, TO><<<blocks, 256, 0, STREAM>>>(static_cast<const TI*>(x), static_cast<TO*>(y), mean, invstd,
@@ -401,6 +422,18 @@ extern "C" int icgan_bn_bwd_reduce(const void* x, const void* dy, const float* m
   ICGAN_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * B * C, STREAM));
   ICGAN_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * B * C, STREAM));
   const int HW = H * W;
+  if (x_dtype == ICGAN_BF16 && dy_dtype == ICGAN_BF16 && vec::ok(C)) {
+    int vs = ceil_div(8 * num_sms(), B);
+    if (vs > (HW + 31) / 32) vs = (HW + 31) / 32;
+    if (vs < 1) vs = 1;
+    const int vppb = (HW + vs - 1) / vs;
+    vs = (HW + vppb - 1) / vppb;
+    vec::bn_bwd_reduce_vec_kernel<<<dim3(static_cast<unsigned>(vs), static_cast<unsigned>(B)), vec::kThreads, 0,
+                                    STREAM>>>(static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), mean,
+                                              invstd, gain, bias, gain_stride, s1, s2, H, W, C, relu, up, vppb);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   int slabs = ceil_div(24 * num_sms(), B);
   if (slabs > (HW + 15) / 16) slabs = (HW + 15) / 16;
   if (slabs < 1) slabs = 1;
@@ -423,6 +456,13 @@ extern "C" int icgan_bn_bwd_apply(const void* x, const void* dy, void* dx, const
                                   int dy_dtype, void* stream) {
   ICGAN_REQUIRE(x && dy && dx && m1 && m2, "icgan_bn_bwd_apply: null pointer");
   const int64_t total = static_cast<int64_t>(B) * H * W * C;
+  if (x_dtype == ICGAN_BF16 && dy_dtype == ICGAN_BF16 && vec::ok(C)) {
+    vec::bn_bwd_apply_vec_kernel<<<vec::blocks_for(total / 8), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), static_cast<vec::bf16*>(dx), mean, invstd,
+        gain, bias, gain_stride, m1, m2, B, H, W, C, relu, up);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = ew_blocks(total);
   DISPATCH_T(x_dtype, TX, {DISPATCH_T(dy_dtype, TG, {
     bn_bwd_apply_kernel<TX, TG, TG><<<blocks, 256, 0, STREAM>>>(static_cast<const TX*>(x), static_cast<const TG*>(dy),
@@ -435,6 +475,12 @@ extern "C" int icgan_bn_bwd_apply(const void* x, const void* dy, void* dx, const
 
 extern "C" int icgan_relu(const void* x, void* y, int64_t n, int dtype, void* stream) {
   ICGAN_REQUIRE(x && y && n > 0, "icgan_relu: bad arguments");
+  if (dtype == ICGAN_BF16 && n % 8 == 0) {
+    vec::ew_vec_kernel<0><<<vec::blocks_for(n / 8), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(x), nullptr, static_cast<vec::bf16*>(y), 0.f, 0.f, nullptr, nullptr, n / 8);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_T(dtype, T, { relu_kernel<T><<<ew_blocks(n), 256, 0, STREAM>>>(static_cast<const T*>(x), static_cast<T*>(y), n); })
   ICGAN_LAUNCH_CHECK();
   return 0;
@@ -442,6 +488,13 @@ extern "C" int icgan_relu(const void* x, void* y, int64_t n, int dtype, void* st
 extern "C" int icgan_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, int ref_dtype, int g_dtype,
                               void* stream) {
   ICGAN_REQUIRE(dy && ref && dx && n > 0, "icgan_relu_bwd: bad arguments");
+  if (ref_dtype == ICGAN_BF16 && g_dtype == ICGAN_BF16 && n % 8 == 0) {
+    vec::ew_vec_kernel<1><<<vec::blocks_for(n / 8), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(dy), static_cast<const vec::bf16*>(ref), static_cast<vec::bf16*>(dx), 0.f, 0.f,
+        nullptr, nullptr, n / 8);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_T(ref_dtype, T, {DISPATCH_T(g_dtype, TG, {
     relu_bwd_kernel<T, TG><<<ew_blocks(n), 256, 0, STREAM>>>(static_cast<const TG*>(dy), static_cast<const T*>(ref),
                                                             static_cast<TG*>(dx), n);
@@ -462,6 +515,13 @@ extern "C" int icgan_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n
 extern "C" int icgan_axpby(const void* a, const void* b, void* out, float alpha, const float* alpha_dev, float beta,
                            const float* beta_dev, int64_t n, int dtype, void* stream) {
   ICGAN_REQUIRE(a && out && n > 0, "icgan_axpby: bad arguments");
+  if (dtype == ICGAN_BF16 && n % 8 == 0) {
+    vec::ew_vec_kernel<3><<<vec::blocks_for(n / 8), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(a), static_cast<const vec::bf16*>(b), static_cast<vec::bf16*>(out), alpha, beta,
+        alpha_dev, beta_dev, n / 8);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_T(dtype, T, {
     axpby_kernel<T><<<ew_blocks(n), 256, 0, STREAM>>>(static_cast<const T*>(a), static_cast<const T*>(b),
                                                      static_cast<T*>(out), alpha, alpha_dev, beta, beta_dev, n);
@@ -483,6 +543,13 @@ extern "C" int icgan_pool2(const void* x, const void* add, void* y, int B, int H
                            int mode, int dtype, void* stream) {
   ICGAN_REQUIRE(x && y, "icgan_pool2: null pointer");
   const int64_t total = static_cast<int64_t>(B) * Hout * Wout * C;
+  if (dtype == ICGAN_BF16 && vec::ok(C)) {
+    vec::pool2_vec_kernel<<<vec::blocks_for(total / 8), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(add), static_cast<vec::bf16*>(y), B, Hout, Wout,
+        C, scale, mode);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_T(dtype, T, {
     pool2_kernel<T><<<ew_blocks(total), 256, 0, STREAM>>>(static_cast<const T*>(x), static_cast<const T*>(add),
                                                          static_cast<T*>(y), B, Hout, Wout, C, scale, mode);
@@ -494,6 +561,13 @@ extern "C" int icgan_unpool2(const void* dy, const void* xref, void* dx, int B, 
                              int mode, int ref_dtype, int g_dtype, void* stream) {
   ICGAN_REQUIRE(dy && dx && (mode == 0 || xref), "icgan_unpool2: null pointer");
   const int64_t total = static_cast<int64_t>(B) * Hout * Wout * C;
+  if (g_dtype == ICGAN_BF16 && (mode == 0 || ref_dtype == ICGAN_BF16) && vec::ok(C)) {
+    vec::unpool2_vec_kernel<<<vec::blocks_for(total / 8), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(dy), static_cast<const vec::bf16*>(xref), static_cast<vec::bf16*>(dx), B, Hout,
+        Wout, C, scale, mode);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_T(ref_dtype, T, {DISPATCH_T(g_dtype, TG, {
     unpool2_kernel<T, TG><<<ew_blocks(total), 256, 0, STREAM>>>(static_cast<const TG*>(dy),
                                                                static_cast<const T*>(xref), static_cast<TG*>(dx), B,
@@ -506,6 +580,17 @@ extern "C" int icgan_unpool2(const void* dy, const void* xref, void* dx, int B, 
 extern "C" int icgan_relu_sumpool(const void* x, float* out, int B, int HW, int C, int dtype, void* stream) {
   ICGAN_REQUIRE(x && out, "icgan_relu_sumpool: null pointer");
   ICGAN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * B * C, STREAM));
+  if (dtype == ICGAN_BF16 && vec::ok(C)) {
+    int vs = ceil_div(4 * num_sms(), B);
+    if (vs > (HW + 15) / 16) vs = (HW + 15) / 16;
+    if (vs < 1) vs = 1;
+    const int vppb = (HW + vs - 1) / vs;
+    vs = (HW + vppb - 1) / vppb;
+    vec::relu_sumpool_vec_kernel<<<dim3(static_cast<unsigned>(vs), static_cast<unsigned>(B)), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(x), out, HW, C, vppb);
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   int slabs = ceil_div(2 * num_sms(), B);
   if (slabs > HW) slabs = HW;
   if (slabs < 1) slabs = 1;
