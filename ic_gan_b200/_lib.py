@@ -31,12 +31,13 @@ class IcganSnLayer(C.Structure):
 
 # name -> argtypes (all return int). Mirrors include/icgan_b200.h one to one; tests check the two stay in sync.
 SIGNATURES = {
-    "icgan_conv2d_tc": [vp, vp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_conv2d_tc": [vp, vp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_tc": [vp, vp, fp, i32, i32, i32, i32, i32, i32, vp],
-    "icgan_conv2d_simt": [vp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_conv2d_simt": [vp, fp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_simt": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
-    "icgan_conv2d_small": [vp, fp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_conv2d_small": [vp, fp, fp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_small": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_im2col_small": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_channel_sum": [vp, fp, i64, i32, i32, vp],
     "icgan_nhwc_to_cnhw": [vp, vp, i64, i32, i32, vp],
     "icgan_sn_power_iteration": [vp, i32, i32, i32, f32, i32, vp],

@@ -18,8 +18,9 @@ struct SimtConvParams {
 
 template <typename TIn, typename TOut, typename TRes>
 __global__ void __launch_bounds__(256)
-conv_simt_kernel(const TIn* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
-                 const TRes* __restrict__ res, TOut* __restrict__ y, SimtConvParams p) {
+conv_simt_kernel(const TIn* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ alpha_p,
+                 const float* __restrict__ bias, const TRes* __restrict__ res, TOut* __restrict__ y, SimtConvParams p) {
+  const float alpha = alpha_p ? *alpha_p : 1.f;
   __shared__ float As[TK][TP + 4];
   __shared__ float Bs[TK][TC + 4];
   const int tid = threadIdx.x;
@@ -94,7 +95,7 @@ conv_simt_kernel(const TIn* __restrict__ x, const float* __restrict__ wk, const 
     for (int j = 0; j < 4; ++j) {
       const int co = co0 + tx * 4 + j;
       if (co >= p.Cout) continue;
-      float v = acc[i][j];
+      float v = alpha * acc[i][j];
       if (bias) v += bias[co];
       if (res) v += ld_as_float(res, rp * p.Cout + co);
       if (p.act == ICGAN_ACT_RELU) v = fmaxf(v, 0.f);
@@ -195,11 +196,11 @@ __global__ void channel_sum_kernel(const T* __restrict__ x, float* __restrict__ 
 }
 
 template <typename TIn, typename TOut, typename TRes>
-static int launch_conv_simt(const void* x, const float* wk, const float* bias, const void* res, void* y,
-                            const SimtConvParams& p, cudaStream_t s) {
+static int launch_conv_simt(const void* x, const float* wk, const float* alpha, const float* bias, const void* res,
+                            void* y, const SimtConvParams& p, cudaStream_t s) {
   const int64_t P = static_cast<int64_t>(p.B) * p.Hout * p.Wout;
   dim3 grid(static_cast<unsigned>((P + TP - 1) / TP), static_cast<unsigned>((p.Cout + TC - 1) / TC));
-  conv_simt_kernel<TIn, TOut, TRes><<<grid, 256, 0, s>>>(static_cast<const TIn*>(x), wk, bias,
+  conv_simt_kernel<TIn, TOut, TRes><<<grid, 256, 0, s>>>(static_cast<const TIn*>(x), wk, alpha, bias,
                                                          static_cast<const TRes*>(res), static_cast<TOut*>(y), p);
   ICGAN_LAUNCH_CHECK();
   return 0;
@@ -209,9 +210,10 @@ static int launch_conv_simt(const void* x, const float* wk, const float* bias, c
 
 using namespace icgan;
 
-extern "C" int icgan_conv2d_simt(const void* x, const float* wk, const float* bias, const void* residual, void* y,
-                                 int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad, int in_dtype,
-                                 int out_dtype, int res_dtype, int res_shift, int act, void* stream) {
+extern "C" int icgan_conv2d_simt(const void* x, const float* wk, const float* alpha_dev, const float* bias,
+                                 const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                                 int stride, int pad, int in_dtype, int out_dtype, int res_dtype, int res_shift, int act,
+                                 void* stream) {
   ICGAN_REQUIRE(x && wk && y, "icgan_conv2d_simt: null pointer");
   ICGAN_REQUIRE(ksize >= 1 && ksize <= 7 && stride >= 1 && pad >= 0, "icgan_conv2d_simt: bad ksize/stride/pad");
   SimtConvParams p{};
@@ -223,14 +225,14 @@ extern "C" int icgan_conv2d_simt(const void* x, const float* wk, const float* bi
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int ib = in_dtype == ICGAN_BF16, ob = out_dtype == ICGAN_BF16, rb = res_dtype == ICGAN_BF16;
   typedef __nv_bfloat16 bf;
-  if (!ib && !ob && !rb) return launch_conv_simt<float, float, float>(x, wk, bias, residual, y, p, s);
-  if (ib && ob && rb) return launch_conv_simt<bf, bf, bf>(x, wk, bias, residual, y, p, s);
-  if (ib && !ob && !rb) return launch_conv_simt<bf, float, float>(x, wk, bias, residual, y, p, s);
-  if (ib && !ob && rb) return launch_conv_simt<bf, float, bf>(x, wk, bias, residual, y, p, s);
-  if (ib && ob && !rb) return launch_conv_simt<bf, bf, float>(x, wk, bias, residual, y, p, s);
-  if (!ib && ob && !rb) return launch_conv_simt<float, bf, float>(x, wk, bias, residual, y, p, s);
-  if (!ib && ob && rb) return launch_conv_simt<float, bf, bf>(x, wk, bias, residual, y, p, s);
-  return launch_conv_simt<float, float, bf>(x, wk, bias, residual, y, p, s);
+  if (!ib && !ob && !rb) return launch_conv_simt<float, float, float>(x, wk, alpha_dev, bias, residual, y, p, s);
+  if (ib && ob && rb) return launch_conv_simt<bf, bf, bf>(x, wk, alpha_dev, bias, residual, y, p, s);
+  if (ib && !ob && !rb) return launch_conv_simt<bf, float, float>(x, wk, alpha_dev, bias, residual, y, p, s);
+  if (ib && !ob && rb) return launch_conv_simt<bf, float, bf>(x, wk, alpha_dev, bias, residual, y, p, s);
+  if (ib && ob && !rb) return launch_conv_simt<bf, bf, float>(x, wk, alpha_dev, bias, residual, y, p, s);
+  if (!ib && ob && !rb) return launch_conv_simt<float, bf, float>(x, wk, alpha_dev, bias, residual, y, p, s);
+  if (!ib && ob && rb) return launch_conv_simt<float, bf, bf>(x, wk, alpha_dev, bias, residual, y, p, s);
+  return launch_conv_simt<float, float, bf>(x, wk, alpha_dev, bias, residual, y, p, s);
 }
 
 extern "C" int icgan_conv2d_wgrad_simt(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin,

@@ -17,8 +17,9 @@ struct SmallConvParams {
 // ---- Cin small: y[p][co] = act(sum_{tap,ci<CS} x[p+tap][ci] * w[co][tap][ci] + bias[co]); thread = 8 out channels
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-conv_small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
-                      TO* __restrict__ y, SmallConvParams p) {
+conv_small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ alpha_p,
+                      const float* __restrict__ bias, TO* __restrict__ y, SmallConvParams p) {
+  const float alpha = alpha_p ? *alpha_p : 1.f;
   extern __shared__ float wsm[];  // [tap][ci][j<8][group]: lanes with consecutive groups hit consecutive banks
   const int taps = p.ksz * p.ksz;
   const int groups = (p.Cout + 7) / 8;
@@ -38,7 +39,7 @@ conv_small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ wk, co
     const int co0 = g * 8;
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (bias && co0 + j < p.Cout) ? bias[co0 + j] : 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int tap = 0; tap < taps; ++tap) {
       const int ih = h + tap / p.ksz - p.pad, iw = w + tap % p.ksz - p.pad;
       if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) continue;
@@ -53,7 +54,7 @@ conv_small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ wk, co
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (co0 + j >= p.Cout) break;
-      float v = acc[j];
+      float v = alpha * acc[j] + (bias ? bias[co0 + j] : 0.f);
       if (p.act == ICGAN_ACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == ICGAN_ACT_TANH) v = tanhf(v);
       st_from_float(y, pix * p.Cout + co0 + j, v);
@@ -64,8 +65,9 @@ conv_small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ wk, co
 // ---- Cout small: one warp per output pixel, lanes stride over Cin, warp-shuffle reduction of the CS sums
 template <typename TI, typename TO, int CS>
 __global__ void __launch_bounds__(256)
-conv_small_cout_kernel(const TI* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
-                       TO* __restrict__ y, SmallConvParams p) {
+conv_small_cout_kernel(const TI* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ alpha_p,
+                       const float* __restrict__ bias, TO* __restrict__ y, SmallConvParams p) {
+  const float alpha = alpha_p ? *alpha_p : 1.f;
   extern __shared__ float wsm[];  // [co][tap][ci] (as given)
   const int taps = p.ksz * p.ksz;
   for (int i = threadIdx.x; i < CS * taps * p.Cin; i += blockDim.x) wsm[i] = i < p.Cout * taps * p.Cin ? wk[i] : 0.f;
@@ -97,7 +99,7 @@ conv_small_cout_kernel(const TI* __restrict__ x, const float* __restrict__ wk, c
       float v = 0.f;
 #pragma unroll
       for (int c = 0; c < CS; ++c)
-        if (lane == c) v = acc[c];
+        if (lane == c) v = alpha * acc[c];
       if (bias) v += bias[lane];
       if (p.act == ICGAN_ACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == ICGAN_ACT_TANH) v = tanhf(v);
@@ -150,6 +152,36 @@ __global__ void wgrad_small_kernel(const TB* __restrict__ big, const TS* __restr
   }
 }
 
+// out[p][j] = x[p + tap(j)][ci(j)] for j = tap*Cs + ci < k*k*Cs, else 0   (bf16 out; thread = 8 output columns)
+template <typename TI>
+__global__ void im2col_small_kernel(const TI* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                    int Cs, int ksz, int KP) {
+  const int groups = KP >> 3, pad = ksz / 2, valid = ksz * ksz * Cs;
+  const int64_t total = static_cast<int64_t>(B) * H * W * groups;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(t % groups);
+    const int64_t pix = t / groups;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const int64_t n = pix / (static_cast<int64_t>(H) * W);
+    uint4 pk;
+    __nv_bfloat16* v = reinterpret_cast<__nv_bfloat16*>(&pk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = g * 8 + i;
+      float val = 0.f;
+      if (j < valid) {
+        const int tap = j / Cs, ci = j - tap * Cs;
+        const int ih = h + tap / ksz - pad, iw = w + tap % ksz - pad;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = ld_as_float(x, ((n * H + ih) * W + iw) * Cs + ci);
+      }
+      v[i] = __float2bfloat16_rn(val);
+    }
+    *reinterpret_cast<uint4*>(out + pix * KP + g * 8) = pk;
+  }
+}
+
 }  // namespace icgan
 
 using namespace icgan;
@@ -163,8 +195,9 @@ using namespace icgan;
     __VA_ARGS__                  \
   }
 
-extern "C" int icgan_conv2d_small(const void* x, const float* wk, const float* bias, void* y, int B, int H, int W,
-                                  int Cin, int Cout, int ksize, int in_dtype, int out_dtype, int act, void* stream) {
+extern "C" int icgan_conv2d_small(const void* x, const float* wk, const float* alpha_dev, const float* bias, void* y,
+                                  int B, int H, int W, int Cin, int Cout, int ksize, int in_dtype, int out_dtype, int act,
+                                  void* stream) {
   ICGAN_REQUIRE(x && wk && y, "icgan_conv2d_small: null pointer");
   ICGAN_REQUIRE(ksize == 1 || ksize == 3, "icgan_conv2d_small: ksize must be 1 or 3");
   ICGAN_REQUIRE(Cin <= kMaxSmall || Cout <= kMaxSmall, "icgan_conv2d_small: needs Cin<=4 or Cout<=4 (got %d, %d)", Cin,
@@ -180,7 +213,7 @@ extern "C" int icgan_conv2d_small(const void* x, const float* wk, const float* b
     if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
     DISPATCH_T(in_dtype, TI, {DISPATCH_T(out_dtype, TO, {
       conv_small_cin_kernel<TI, TO><<<static_cast<unsigned>(blocks), 256, smem, STREAM>>>(
-          static_cast<const TI*>(x), wk, bias, static_cast<TO*>(y), p);
+          static_cast<const TI*>(x), wk, alpha_dev, bias, static_cast<TO*>(y), p);
     })})
   } else {
     const size_t smem = sizeof(float) * static_cast<size_t>(kMaxSmall) * taps * Cin;
@@ -189,7 +222,7 @@ extern "C" int icgan_conv2d_small(const void* x, const float* wk, const float* b
     if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
     DISPATCH_T(in_dtype, TI, {DISPATCH_T(out_dtype, TO, {
       conv_small_cout_kernel<TI, TO, kMaxSmall><<<static_cast<unsigned>(blocks), 256, smem, STREAM>>>(
-          static_cast<const TI*>(x), wk, bias, static_cast<TO*>(y), p);
+          static_cast<const TI*>(x), wk, alpha_dev, bias, static_cast<TO*>(y), p);
     })})
   }
   ICGAN_LAUNCH_CHECK();
@@ -221,6 +254,21 @@ extern "C" int icgan_conv2d_wgrad_small(const void* x, const void* dy, float* dw
           static_cast<const TB*>(x), static_cast<const TS*>(dy), dwk, B, H, W, Cb, Cs, ksize, 0, ppb);
     })})
   }
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_im2col_small(const void* x, void* out, int B, int H, int W, int Cs, int ksize, int KP, int in_dtype,
+                                  void* stream) {
+  ICGAN_REQUIRE(x && out && Cs >= 1 && Cs <= kMaxSmall && KP % 8 == 0 && KP >= ksize * ksize * Cs,
+                "icgan_im2col_small: bad arguments (Cs=%d KP=%d)", Cs, KP);
+  const int64_t total = static_cast<int64_t>(B) * H * W * (KP / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
+  DISPATCH_T(in_dtype, TI, {
+    im2col_small_kernel<TI><<<static_cast<unsigned>(blocks), 256, 0, STREAM>>>(
+        static_cast<const TI*>(x), static_cast<__nv_bfloat16*>(out), B, H, W, Cs, ksize, KP);
+  })
   ICGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -117,6 +117,7 @@ struct TcConvParams {
   void* y;
   const float* bias;
   const void* res;
+  const float* alpha;  // device scalar multiplied into the accumulator (1/sigma of spectral norm), may be null
 };
 
 struct TileCoord {
@@ -257,6 +258,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int row = q * 32 + lane;
     const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
+    const float alpha = p.alpha ? *p.alpha : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -279,7 +281,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (valid && co < p.Cout) {
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[half * 8 + j]);
+            for (int j = 0; j < 8; ++j) v[j] = alpha * __uint_as_float(r[half * 8 + j]);
             if (p.bias) {
               const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
               const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
@@ -523,9 +525,9 @@ __global__ void nhwc_to_cnhw_kernel(const T* __restrict__ x, __nv_bfloat16* __re
 
 using namespace icgan;
 
-extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* bias, const void* residual, void* y, int B,
-                               int H, int W, int Cin, int Cout, int ksize, int out_dtype, int res_dtype, int res_shift,
-                               int act, void* stream) {
+extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha_dev, const float* bias,
+                               const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                               int out_dtype, int res_dtype, int res_shift, int act, void* stream) {
   ICGAN_REQUIRE(x && wk && y, "icgan_conv2d_tc: null pointer");
   ICGAN_REQUIRE(ksize == 1 || ksize == 3, "icgan_conv2d_tc: ksize must be 1 or 3 (got %d)", ksize);
   ICGAN_REQUIRE(B > 0 && H > 0 && W > 0, "icgan_conv2d_tc: bad shape B=%d H=%d W=%d", B, H, W);
@@ -574,7 +576,7 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* bias,
   p.res_bf16 = res_dtype == ICGAN_BF16;
   p.res_shift = res_shift;
   p.act = act;
-  p.y = y; p.bias = bias; p.res = residual;
+  p.y = y; p.bias = bias; p.res = residual; p.alpha = alpha_dev;
 
   CUtensorMap tmA, tmB;
   {

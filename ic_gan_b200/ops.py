@@ -34,26 +34,36 @@ def _timed(kernel: str, flops: float, fn):
     return out
 
 
-def _tc_ok(x: Tensor, cin: int, cout: int, k: int) -> bool:
-    return x.dtype == torch.bfloat16 and cin % 16 == 0 and cout % 8 == 0 and k in (1, 3)
-
-
 # ===================================================================================== spectral-norm state
+# Operand copies of a conv weight are rebuilt when the master weight may have changed.  Signals: the tensor version
+# counter (load_state_dict, in-place ops), a process-wide counter bumped after EVERY optimizer step (fused optimizers
+# do not bump tensor versions), eval mode (always rebuild: EMA copies are written through .data), or invalidate_operands().
+_WEIGHT_EPOCH = [0]
+
+
+def invalidate_operands(*_args, **_kwargs) -> None:
+    _WEIGHT_EPOCH[0] += 1
+
+
+torch.optim.optimizer.register_optimizer_step_post_hook(invalidate_operands)
+
+
 class SNState:
-    """Per-layer device state for spectral norm + the operand copies of the (scaled) weight.
+    """Per-layer device state for spectral norm + the operand copies of the weight the conv kernels read.
 
     Restates SN.W_ (BigGAN_PyTorch/layers.py:98-112): one power iteration per forward, sigma = u'^T W v, weight / sigma.
-    `weight` is the float32 master parameter in the reference layout (OIHW / [out,in]); `u`, `sv` are the module's
-    registered buffers `u0`, `sv0` (same names/shapes as the reference, so checkpoints load unchanged)."""
+    The division is folded into the kernels' epilogues as a device scalar alpha = 1/sigma, so the (unscaled) operand
+    copies are rebuilt only when the master weight actually changed (optimizer step / load_state_dict), tracked with
+    the tensor version counter.  `weight` is the float32 master parameter in the reference layout (OIHW / [out,in]);
+    `u0`, `sv0` are the module's registered buffers (same names/shapes as the reference)."""
 
     def __init__(self, module, kind: str, use_sn: bool = True):
         self.module = module
         self.kind = kind  # "conv" | "linear" | "embed"
         self.use_sn = use_sn
         self.fresh = False
-        self.aux = None  # [v(cols) | u_new(rows) | sigma(2) | scratch(2)]
-        self.wk_fwd = self.wk_dgrad = self.wk_fwd32 = None
         self.key = None
+        self.version = None
 
     # -- buffers -------------------------------------------------------------------------------------------------
     def _ensure(self, compute_dtype):
@@ -62,46 +72,73 @@ class SNState:
         key = (w.device, w.data_ptr(), compute_dtype, self.module.u0.data_ptr() if self.use_sn else 0)
         if self.key == key:
             return
-        self.key = key
+        self.key, self.version = key, None
         self.rows, self.cols = rows, cols
         self.aux = torch.zeros(cols + rows + 4, device=w.device, dtype=torch.float32)
         self.v = self.aux[:cols]
         self.u_new = self.aux[cols:cols + rows]
         self.sigma = self.aux[cols + rows:cols + rows + 2]
         self.scratch = self.aux[cols + rows + 2:]
-        self.sigma[0] = 1.0
-        self.sigma[1] = 1.0
-        if self.kind == "conv":
-            co, ci, k, _ = w.shape
-            self.wk_fwd = torch.empty(co, k, k, ci, device=w.device, dtype=compute_dtype)
-            self.wk_dgrad = torch.empty(ci, k, k, co, device=w.device, dtype=compute_dtype)
-            # image-side layers (Cin=3 / Cout=3) run on the CUDA-core kernel, which reads float32 weights
-            self.need32 = compute_dtype != torch.float32 and not (ci % 16 == 0 and co % 8 == 0)
-            self.need32d = compute_dtype != torch.float32 and not (co % 16 == 0 and ci % 8 == 0)
-            self.wk_fwd32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32) if self.need32 else None
-            self.wk_dgrad32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32) if self.need32d else None
-        else:
-            self.wk_fwd = torch.empty(rows, cols, device=w.device, dtype=torch.float32)
+        self.sigma.fill_(1.0)
+        self.alpha = self.sigma[1:] if self.use_sn else None  # device scalar 1/sigma
+        self.wk_fwd = self.wk_dgrad = self.wk_fwd32 = self.wk_dgrad32 = None
+        self.mode = self.mode_d = "plain"
+        if self.kind != "conv":
+            return
+        co, ci, k, _ = w.shape
+        dev, bf = w.device, compute_dtype == torch.bfloat16
+        # forward operand: how the layer runs (see _conv_forward)
+        #   "tc"    tensor-core implicit GEMM on [Cout,k,k,Cin] bf16
+        #   "col"   Cin<=4 (RGB in): explicit im2col to KP=16/32 columns, then the tensor-core kernel as a 1x1 conv
+        #   "pad8"  Cout<=4 (RGB out): weight rows zero-padded to 8, output sliced back
+        #   "f32"   CUDA-core fp32 kernels (parity mode, or shapes the tensor-core path does not take)
+        def pick(cin, cout):
+            if bf and cin % 16 == 0 and cout % 8 == 0:
+                return "tc"
+            if bf and cin <= 4 and cout % 8 == 0:
+                return "col"
+            if bf and cout <= 4 and cin % 16 == 0:
+                return "pad8"
+            return "f32"
+        self.mode, self.mode_d = pick(ci, co), pick(co, ci)
+        self.kp = (k * k * ci + 15) // 16 * 16   # im2col width of the forward / of the dgrad ("col" modes)
+        self.kp_d = (k * k * co + 15) // 16 * 16
 
     def descriptor(self) -> L.IcganSnLayer:
         m = self.module
         return L.IcganSnLayer(ptr(m.weight), ptr(m.u0), ptr(self.v), ptr(self.u_new), ptr(self.sigma), ptr(self.scratch),
                               self.rows, self.cols)
 
+    def _operand(self, wk: Tensor, mode: str, kp: int):
+        """[Cout,k,k,Cin] float32 -> operand tensor for `mode`."""
+        co, k, _, ci = wk.shape
+        if mode == "tc":
+            return wk.to(torch.bfloat16)
+        if mode == "col":
+            out = torch.zeros(co, 1, 1, kp, device=wk.device, dtype=torch.bfloat16)
+            out.view(co, kp)[:, :k * k * ci] = wk.reshape(co, -1)
+            return out
+        if mode == "pad8":
+            out = torch.zeros(8, k, k, ci, device=wk.device, dtype=torch.bfloat16)
+            out[:co] = wk
+            return out
+        return wk
+
     def prepare(self):
-        """Scaled operand copies from the master weight (after sigma is known)."""
+        """(Re)build the operand copies iff the master weight changed since the last build."""
         w = self.module.weight
-        inv = ptr(self.sigma[1:]) if self.use_sn else None
-        if self.kind == "conv":
-            co, ci, k, _ = w.shape
-            call("icgan_sn_prepare_weight", ptr(w), inv, ptr(self.wk_fwd), ptr(self.wk_dgrad), co, ci, k,
-                 dt(self.wk_fwd), stream_ptr())
-            if self.wk_fwd32 is not None or self.wk_dgrad32 is not None:
-                call("icgan_sn_prepare_weight", ptr(w), inv, ptr(self.wk_fwd32), ptr(self.wk_dgrad32), co, ci, k, L.F32,
-                     stream_ptr())
-        else:
-            call("icgan_sn_prepare_weight", ptr(w), inv, ptr(self.wk_fwd), None, self.rows, self.cols, 1, L.F32,
-                 stream_ptr())
+        if self.kind != "conv":
+            return
+        stamp = (w._version, _WEIGHT_EPOCH[0])
+        if self.version == stamp and self.module.training:
+            return
+        self.version = stamp
+        co, ci, k, _ = w.shape
+        f32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32)
+        d32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32)
+        call("icgan_sn_prepare_weight", ptr(w), None, ptr(f32), ptr(d32), co, ci, k, L.F32, stream_ptr())
+        self.wk_fwd = self._operand(f32, self.mode, self.kp)
+        self.wk_dgrad = self._operand(d32, self.mode_d, self.kp_d)
 
     def weight_grad(self, G: Tensor) -> Tensor:
         """dL/dW (master layout) from G = dL/d(W/sigma) given in operand layout (float32)."""
@@ -120,7 +157,8 @@ class SNState:
 
 
 def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype, table_cache: dict) -> None:
-    """One batched power-iteration step + operand preparation for all given layers (start of every forward)."""
+    """One batched power-iteration step for all given layers + operand rebuild where weights changed
+    (start of every forward)."""
     if not states:
         return
     for s in states:
@@ -146,30 +184,63 @@ def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype,
 
 
 # ===================================================================================== convolution
-def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: int, out_dtype, dgrad: bool = False):
-    B, H, W, cin = x.shape
-    if not dgrad:
-        wk, wk32 = st.wk_fwd, st.wk_fwd32
-    else:
-        wk, wk32 = st.wk_dgrad, st.wk_dgrad32
-    cout, k = wk.shape[0], wk.shape[1]
-    y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
+def _tc_conv(x, wk, alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act):
     rdt = dt(residual) if residual is not None else L.F32
-    if _tc_ok(x, cin, cout, k) and wk.dtype == torch.bfloat16:
-        _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
-               lambda: call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k,
-                            dt(y), rdt, res_shift, act, stream_ptr()))
-    elif min(cin, cout) <= 4 and residual is None:
-        w32 = wk if wk.dtype == torch.float32 else wk32
-        call("icgan_conv2d_small", ptr(x), ptr(w32), ptr(bias), ptr(y), B, H, W, cin, cout, k, dt(x), dt(y), act,
-             stream_ptr())
+    _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
+           lambda: call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(alpha), ptr(bias), ptr(residual), ptr(y), B, H, W, cin,
+                        cout, k, dt(y), rdt, res_shift, act, stream_ptr()))
+
+
+def _im2col(x: Tensor, k: int, kp: int) -> Tensor:
+    B, H, W, cs = x.shape
+    out = torch.empty(B, H, W, kp, device=x.device, dtype=torch.bfloat16)
+    call("icgan_im2col_small", ptr(x), ptr(out), B, H, W, cs, k, kp, dt(x), stream_ptr())
+    return out
+
+
+def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: int, out_dtype, dgrad: bool = False,
+                  keep: Optional[dict] = None):
+    """act(alpha * conv(x, operand) + bias + residual); `keep` receives tensors worth saving for the backward."""
+    B, H, W, cin = x.shape
+    wk, mode, kp = (st.wk_fwd, st.mode, st.kp) if not dgrad else (st.wk_dgrad, st.mode_d, st.kp_d)
+    w = st.module.weight
+    cout, k = (w.shape[0], w.shape[2]) if not dgrad else (w.shape[1], w.shape[2])
+    if mode == "tc":
+        y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
+        _tc_conv(x, wk, st.alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act)
+        return y
+    if mode == "col":  # RGB-side input: im2col (27 -> 32 columns) + tensor-core 1x1
+        xcol = _im2col(x, k, kp)
+        if keep is not None:
+            keep["xcol"] = xcol
+        y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
+        _tc_conv(xcol, wk, st.alpha, bias, residual, y, B, H, W, kp, cout, 1, res_shift, act)
+        return y
+    if mode == "pad8":  # RGB-side output: 8 padded output channels, first `cout` kept
+        if residual is not None:
+            raise RuntimeError("residual is not supported on <=4-channel outputs")
+        b8 = None
+        if bias is not None:
+            b8 = torch.zeros(8, device=x.device, dtype=torch.float32)
+            b8[:cout] = bias
+        y8 = torch.empty(B, H, W, 8, device=x.device, dtype=out_dtype)
+        _tc_conv(x, wk, st.alpha, b8, None, y8, B, H, W, cin, 8, k, 0, act)
+        return y8[..., :cout].contiguous()
+    # float32 CUDA-core kernels
+    y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
+    if min(cin, cout) <= 4 and residual is None:
+        call("icgan_conv2d_small", ptr(x), ptr(wk), ptr(st.alpha), ptr(bias), ptr(y), B, H, W, cin, cout, k, dt(x), dt(y),
+             act, stream_ptr())
     else:
-        w32 = wk if wk.dtype == torch.float32 else wk32
-        if w32 is None:
-            raise RuntimeError(f"no float32 operand copy for conv {cin}->{cout} (dtype {x.dtype})")
-        call("icgan_conv2d_simt", ptr(x), ptr(w32), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k, 1, k // 2,
-             dt(x), dt(y), rdt, res_shift, act, stream_ptr())
+        rdt = dt(residual) if residual is not None else L.F32
+        call("icgan_conv2d_simt", ptr(x), ptr(wk), ptr(st.alpha), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k,
+             1, k // 2, dt(x), dt(y), rdt, res_shift, act, stream_ptr())
     return y
+
+
+def _wgrad_tc(x, dy, G, B, H, W, cin, cout, k):
+    _timed("tc_wgrad_kernel", 2.0 * B * H * W * cout * cin * k * k,
+           lambda: call("icgan_conv2d_wgrad_tc", ptr(x), ptr(dy), ptr(G), B, H, W, cin, cout, k, stream_ptr()))
 
 
 class SNConvFn(torch.autograd.Function):
@@ -180,21 +251,22 @@ class SNConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, st: SNState, res_shift: int, act: int, out_dtype):
         x = x.contiguous()
-        y = _conv_forward(x, st, bias, residual, res_shift, act, out_dtype)
+        keep = {}
+        y = _conv_forward(x, st, bias, residual, res_shift, act, out_dtype, keep=keep)
         ctx.st, ctx.res_shift, ctx.act = st, res_shift, act
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.res_dtype = residual.dtype if residual is not None else None
-        ctx.save_for_backward(x, y if act != L.ACT_NONE else None)
+        ctx.save_for_backward(x, y if act != L.ACT_NONE else None, keep.get("xcol"))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
+        x, y, xcol = ctx.saved_tensors
         st: SNState = ctx.st
         dy = dy.contiguous()
         B, H, W, cout = dy.shape
         cin = x.shape[3]
-        k = st.wk_fwd.shape[1] if st.kind == "conv" else 1
+        k = st.module.weight.shape[2]
         n = dy.numel()
         if ctx.act == L.ACT_RELU:
             g = torch.empty_like(dy)
@@ -216,23 +288,31 @@ class SNConvFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.zeros(cout, device=dy.device, dtype=torch.float32)
             call("icgan_channel_sum", ptr(dy), ptr(db), B * H * W, cout, dt(dy), stream_ptr())
+        dyc = dy if dy.dtype == x.dtype else dy.to(x.dtype)  # gradients travel in the activation dtype
         if ctx.needs_input_grad[0]:
-            gdt = x.dtype
-            dyc = dy if dy.dtype == x.dtype else dy.to(x.dtype)
-            dx = _conv_forward(dyc, st, None, None, 0, L.ACT_NONE, gdt, dgrad=True)
+            dx = _conv_forward(dyc, st, None, None, 0, L.ACT_NONE, x.dtype, dgrad=True)
         if ctx.needs_input_grad[1]:
-            G = torch.zeros(cout, k, k, cin, device=dy.device, dtype=torch.float32)
-            dyc = dy if dy.dtype == x.dtype else dy.to(x.dtype)
-            if x.dtype == torch.bfloat16 and cin % 16 == 0 and cout % 8 == 0:
-                _timed("tc_wgrad_kernel", 2.0 * B * H * W * cout * cin * k * k,
-                       lambda: call("icgan_conv2d_wgrad_tc", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k,
-                                    stream_ptr()))
-            elif min(cin, cout) <= 4:
-                call("icgan_conv2d_wgrad_small", ptr(x), ptr(dy), ptr(G), B, H, W, cin, cout, k, dt(x), dt(dy),
-                     stream_ptr())
+            if st.mode == "tc":
+                G = torch.zeros(cout, k, k, cin, device=dy.device, dtype=torch.float32)
+                _wgrad_tc(x, dyc, G, B, H, W, cin, cout, k)
+            elif st.mode == "col":
+                Gc = torch.zeros(cout, st.kp, device=dy.device, dtype=torch.float32)
+                _wgrad_tc(xcol if xcol is not None else _im2col(x, k, st.kp), dyc, Gc, B, H, W, st.kp, cout, 1)
+                G = Gc[:, :k * k * cin].reshape(cout, k, k, cin).contiguous()
+            elif st.mode == "pad8":
+                dy8 = torch.zeros(B, H, W, 8, device=dy.device, dtype=x.dtype)
+                dy8[..., :cout] = dyc
+                G8 = torch.zeros(8, k, k, cin, device=dy.device, dtype=torch.float32)
+                _wgrad_tc(x, dy8, G8, B, H, W, cin, 8, k)
+                G = G8[:cout].contiguous()
             else:
-                call("icgan_conv2d_wgrad_simt", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, 1, k // 2, dt(x),
-                     stream_ptr())
+                G = torch.zeros(cout, k, k, cin, device=dy.device, dtype=torch.float32)
+                if min(cin, cout) <= 4:
+                    call("icgan_conv2d_wgrad_small", ptr(x), ptr(dy), ptr(G), B, H, W, cin, cout, k, dt(x), dt(dy),
+                         stream_ptr())
+                else:
+                    call("icgan_conv2d_wgrad_simt", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, 1, k // 2, dt(x),
+                         stream_ptr())
             dW = st.weight_grad(G)
         return dx, dW, db, dres, None, None, None, None
 
@@ -245,7 +325,7 @@ def _gemm(A, B_, Cm, M, N, K, sa, sb, sc, alpha=1.0, alpha_dev=None, beta=0.0, b
 
 
 class SNLinearFn(torch.autograd.Function):
-    """y = x (W/sigma)^T + b  (layers.SNLinear.forward, layers.py:164-165); all float32."""
+    """y = x (W/sigma)^T + b  (layers.SNLinear.forward, layers.py:164-165); all float32; 1/sigma is the GEMM's alpha."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, st: SNState):
@@ -253,15 +333,14 @@ class SNLinearFn(torch.autograd.Function):
         Bn, K = x.shape
         N = weight.shape[0]
         y = torch.empty(Bn, N, device=x.device, dtype=torch.float32)
-        # A = x [Bn,K]; B[k][n] = wk[n][k]
-        _gemm(x, st.wk_fwd, y, Bn, N, K, (K, 1), (1, K), (N, 1), bias=bias)
+        _gemm(x, weight, y, Bn, N, K, (K, 1), (1, K), (N, 1), alpha_dev=st.alpha, bias=bias)  # B[k][n] = W[n][k]
         ctx.st, ctx.has_bias = st, bias is not None
-        ctx.save_for_backward(x)
+        ctx.save_for_backward(x, weight)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
+        x, weight = ctx.saved_tensors
         st: SNState = ctx.st
         dy = dy.contiguous().float()
         Bn, K = x.shape
@@ -269,10 +348,10 @@ class SNLinearFn(torch.autograd.Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _gemm(dy, st.wk_fwd, dx, Bn, K, N, (N, 1), (K, 1), (K, 1))  # dx = dy @ W~
+            _gemm(dy, weight, dx, Bn, K, N, (N, 1), (K, 1), (K, 1), alpha_dev=st.alpha)  # dx = dy @ (W/sigma)
         if ctx.needs_input_grad[1]:
             G = torch.empty(N, K, device=x.device, dtype=torch.float32)
-            _gemm(dy, x, G, N, K, Bn, (1, N), (K, 1), (K, 1))  # G = dy^T @ x
+            _gemm(dy, x, G, N, K, Bn, (1, N), (K, 1), (K, 1))  # G = dy^T @ x = dL/d(W/sigma)
             dW = st.weight_grad(G)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.zeros(N, device=x.device, dtype=torch.float32)
@@ -287,7 +366,8 @@ class SNEmbedFn(torch.autograd.Function):
     def forward(ctx, idx, weight, st: SNState):
         ctx.st = st
         ctx.save_for_backward(idx)
-        return st.wk_fwd.index_select(0, idx)
+        rows = weight.detach().index_select(0, idx)
+        return rows * st.alpha if st.alpha is not None else rows
 
     @staticmethod
     def backward(ctx, dy):

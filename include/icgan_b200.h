@@ -41,10 +41,11 @@ int icgan_version(void);
  * x: [B,H,W,Cin] bf16, wk: [Cout,k,k,Cin] bf16, k in {1,3}, stride 1, pad k/2, Cin%16==0, Cout%8==0, H,W powers of two.
  * out_dtype/res_dtype: ICGAN_F32|ICGAN_BF16. residual may be NULL; res_shift=1 reads residual[n,h/2,w/2,co] from a
  * half-resolution tensor (the nearest-upsampled shortcut of GBlock, layers.py:545-552). bias may be NULL.
+ * alpha_dev (device scalar, may be NULL): the accumulator is scaled by it before bias -- 1/sigma of SN.W_ (layers.py:112).
  * Serves forward, and dgrad when called with the flipped/transposed weight copy. */
-int icgan_conv2d_tc(const void* x, const void* wk, const float* bias, const void* residual, void* y, int B, int H,
-                    int W, int Cin, int Cout, int ksize, int out_dtype, int res_dtype, int res_shift, int act,
-                    void* stream);
+int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha_dev, const float* bias, const void* residual,
+                    void* y, int B, int H, int W, int Cin, int Cout, int ksize, int out_dtype, int res_dtype,
+                    int res_shift, int act, void* stream);
 
 /* Tensor-core weight gradient for 3x3/1x1 stride-1 convs (replaces cudnn_convolution_backward_weight,
  * stylegan2_ada_pytorch/torch_utils/ops/conv2d_gradfix.py:223-227, and ATen's conv backward under BigGAN):
@@ -57,18 +58,22 @@ int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, int B, int 
 /* Generic CUDA-core path (float32 accumulate; any channel counts, e.g. Cin=3 / Cout=3; any stride/pad).
  * H, W are INPUT dims; output is [(H+2*pad-k)/stride+1, ...]. x/y dtype per in_dtype/out_dtype; wk float32
  * [Cout,k,k,Cin]. Same epilogue as icgan_conv2d_tc. */
-int icgan_conv2d_simt(const void* x, const float* wk, const float* bias, const void* residual, void* y, int B, int H,
-                      int W, int Cin, int Cout, int ksize, int stride, int pad, int in_dtype, int out_dtype,
-                      int res_dtype, int res_shift, int act, void* stream);
+int icgan_conv2d_simt(const void* x, const float* wk, const float* alpha_dev, const float* bias, const void* residual,
+                      void* y, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad, int in_dtype,
+                      int out_dtype, int res_dtype, int res_shift, int act, void* stream);
 /* dwk (float32, accumulated) from NHWC x [B,H,W,Cin] and dy [B,Hout,Wout,Cout] of dtype in_dtype. */
 int icgan_conv2d_wgrad_simt(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin, int Cout,
                             int ksize, int stride, int pad, int in_dtype, void* stream);
 /* Image-side layers where Cin<=4 or Cout<=4 (RGB): HBM-bound streaming kernels instead of GEMM tiles. wk float32
  * [Cout,k,k,Cin], k in {1,3}, stride 1, pad k/2; serves forward and (with the dgrad weight copy) dgrad. */
-int icgan_conv2d_small(const void* x, const float* wk, const float* bias, void* y, int B, int H, int W, int Cin,
-                       int Cout, int ksize, int in_dtype, int out_dtype, int act, void* stream);
+int icgan_conv2d_small(const void* x, const float* wk, const float* alpha_dev, const float* bias, void* y, int B, int H,
+                       int W, int Cin, int Cout, int ksize, int in_dtype, int out_dtype, int act, void* stream);
 int icgan_conv2d_wgrad_small(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin, int Cout,
                              int ksize, int x_dtype, int dy_dtype, void* stream);
+/* Explicit im2col of a <=4-channel NHWC tensor: out[p][tap*Cs+ci] = x[p+tap][ci] (zero outside / beyond k*k*Cs),
+ * out bf16 [B,H,W,KP]; lets the RGB-side layers run on icgan_conv2d_tc / icgan_conv2d_wgrad_tc as 1x1 convs. */
+int icgan_im2col_small(const void* x, void* out, int B, int H, int W, int Cs, int ksize, int KP, int in_dtype,
+                       void* stream);
 /* out[c] += sum over pixels of x[p][c]  (bias gradient; NHWC column sums). */
 int icgan_channel_sum(const void* x, float* out, int64_t pixels, int C, int dtype, void* stream);
 

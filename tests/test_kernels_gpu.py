@@ -177,3 +177,27 @@ def test_pool_relu_sumpool_linear(cuda_device, cdt):
     _close(out, outr, 1e-4, "linear fwd")
     _close(xi.grad, xr.grad, 1e-4, "linear dx")
     _close(lin.weight.grad, W.grad, 1e-4, "linear dW through sigma")
+
+
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+def test_operand_copies_follow_weight_updates(cuda_device, cdt):
+    """The bf16/fp32 operand copies are rebuilt lazily (tensor version counter): an optimizer step must be seen."""
+    from ic_gan_b200.biggan import layers
+    torch.manual_seed(5)
+    m = layers.SNConv2d(32, 16, 3, padding=1, eps=1e-6).to(cuda_device)
+    m.compute_dtype = cdt
+    m.eval()
+    x = torch.randn(2, 32, 8, 8, device=cuda_device).to(cdt).float()
+    opt = torch.optim.Adam(m.parameters(), lr=0.05, fused=True)
+    for _ in range(2):
+        y = m(x.to(cdt))
+        W = m.weight.detach()
+        Wm = W.reshape(16, -1)
+        v = F.normalize(m.u0 @ Wm, eps=1e-6)
+        un = F.normalize(v @ Wm.t(), eps=1e-6)
+        ref = F.conv2d(x, W / (v @ Wm.t() @ un.t()).squeeze(), m.bias.detach(), 1, 1)
+        _close(y, ref, TOL[cdt], "forward after weight update")
+        m.train()
+        m(x.to(cdt)).float().pow(2).mean().backward()
+        opt.step()
+        m.eval()
