@@ -45,7 +45,9 @@ def invalidate_operands(*_args, **_kwargs) -> None:
     _WEIGHT_EPOCH[0] += 1
 
 
-torch.optim.optimizer.register_optimizer_step_post_hook(invalidate_operands)
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
+
+_register_step_hook(invalidate_operands)
 
 
 class SNState:
