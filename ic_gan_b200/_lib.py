@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libicgan_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
 _lib: Optional[C.CDLL] = None
@@ -62,6 +62,9 @@ SIGNATURES = {
     "icgan_knn_coarse": [vp, vp, fp, i64, i32, i64, i64, i32, i32, vp, fp, vp],
     "icgan_knn_rerank": [fp, i64, i32, i64, i64, i32, i32, vp, fp, vp, vp, vp, fp, f32, vp],
     "icgan_knn_exact_row": [fp, i64, i32, i64, i32, vp, vp, vp, vp],
+    "icgan_bias_act": [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, f32, f32, f32, i32, vp],
+    "icgan_upfirdn2d": [vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
+                        i32, vp],
     "icgan_gemm_tc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
     "icgan_gemm": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, fp, f32, fp, i32,
                    i32, i32, vp],
@@ -116,6 +119,8 @@ def dt(t) -> int:
         return F32
     if d == torch.bfloat16:
         return BF16
+    if d == torch.float16:
+        return F16  # StyleGAN2 ops only
     raise TypeError(f"unsupported dtype {d}; activations must be float32 or bfloat16")
 
 

@@ -23,6 +23,7 @@ extern "C" {
 
 #define ICGAN_F32 0
 #define ICGAN_BF16 1
+#define ICGAN_F16 2 /* StyleGAN2 ops only */
 
 #define ICGAN_ACT_NONE 0
 #define ICGAN_ACT_RELU 1
@@ -185,6 +186,24 @@ int icgan_knn_rerank(const float* X, int64_t N, int d, int64_t q_begin, int64_t 
 /* Brute-force float64 answer for one row (scratch: N doubles). */
 int icgan_knn_exact_row(const float* X, int64_t N, int d, int64_t row, int k, double* scratch, int64_t* nn_out_row,
                         double* radius_out_row, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * StyleGAN2-ADA native ops (the reference's pybind11 plugins).
+ * ---------------------------------------------------------------------------------------------- */
+/* Replaces `Tensor bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)`
+ * (stylegan2_ada_pytorch/torch_utils/ops/bias_act.cpp:35; kernel bias_act.cu:26-150). Flat over n elements of `dtype`
+ * (ICGAN_F32/BF16/F16); b (same dtype, may be NULL) is indexed by (i / step_b) %% size_b (step_b = prod of dims after
+ * `dim`, valid for dense NCHW and channels-last alike); act = cuda_idx 1..9 of bias_act.py:26-99; grad 0/1/2;
+ * clamp < 0 disables clamping; xref/yref/dy may be NULL ("empty tensor" in the reference). */
+int icgan_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y, int64_t n,
+                   int64_t step_b, int size_b, int grad, int act, float alpha, float gain, float clamp, int dtype,
+                   void* stream);
+/* Replaces `Tensor upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)`
+ * (upfirdn2d.cpp:19; kernels upfirdn2d.cu:32-203). x: [N,C,inH,inW] (channels_last=0) or NHWC memory (=1), f: float32
+ * [fh,fw]; y: [N,C,outH,outW] with outW = (inW*upx+padx0+padx1-fw+downx)/downx (upfirdn2d.cpp:35-36). */
+int icgan_upfirdn2d(const void* x, const float* f, void* y, int N, int C, int inH, int inW, int fh, int fw, int upx,
+                    int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                    int channels_last, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,5 +61,60 @@ def knn_golden(ref, gold):
     print(f"[golden] knn_n1500_k50: oracle sets == reference sklearn sets on {n - mism}/{n} rows")
 
 
+def stylegan_ops_golden(ref, gold):
+    """bias_act / upfirdn2d: the reference's own impl='ref' outputs and autograd gradients (1st and 2nd order)."""
+    import torch
+    from oracle import stylegan_ops_oracle as S
+    sys.path.insert(0, os.path.join(ref, "stylegan2_ada_pytorch"))
+    import warnings
+    warnings.filterwarnings("ignore")
+    from torch_utils.ops import bias_act as RB, upfirdn2d as RU
+    out = {}
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(3, 6, 5, 7, generator=g) * 2
+    b = torch.randn(6, generator=g)
+    gy = torch.randn(3, 6, 5, 7, generator=g)
+    gg = torch.randn(3, 6, 5, 7, generator=g)
+    out["ba_x"], out["ba_b"], out["ba_gy"], out["ba_gg"] = x, b, gy, gg
+    for act in RB.activation_funcs:
+        for tag, kw in (("def", {}), ("clamp", dict(gain=1.7, clamp=1.1, alpha=0.3))):
+            xr, br = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            y = RB.bias_act(xr, br, act=act, impl="ref", **kw)
+            dx, db = torch.autograd.grad(y, [xr, br], gy, create_graph=True)
+            ddx = torch.autograd.grad(dx, xr, gg, allow_unused=True)[0] if dx.requires_grad else None
+            xo, bo = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            yo = S.bias_act(xo, bo, act=act, **kw)
+            dxo, dbo = torch.autograd.grad(yo, [xo, bo], gy, create_graph=True)
+            assert (yo - y).abs().max() <= 1e-6 and (dxo - dx).abs().max() <= 1e-5 and (dbo - db).abs().max() <= 1e-4, act
+            k = f"ba_{act}_{tag}"
+            out[k + "_y"], out[k + "_dx"], out[k + "_db"] = y.detach(), dx.detach(), db.detach()
+            out[k + "_ddx"] = torch.zeros_like(x) if ddx is None else ddx.detach()
+    f = RU.setup_filter([1, 3, 3, 1])
+    assert (f - S.setup_filter([1, 3, 3, 1])).abs().max() == 0
+    out["uf_f"] = f
+    for site in S.UPFIRDN_SITES:
+        hw = 9 if site["odd"] else 8
+        xi = torch.randn(2, 5, hw, hw, generator=g)
+        xr = xi.clone().requires_grad_(True)
+        y = RU.upfirdn2d(xr, f, up=site["up"], down=site["down"], padding=site["padding"], gain=site["gain"], impl="ref")
+        gyy = torch.randn(y.shape, generator=g)
+        dx = torch.autograd.grad(y, xr, gyy)[0]
+        yo = S.upfirdn2d(xi, f, up=site["up"], down=site["down"], padding=site["padding"], gain=site["gain"])
+        assert yo.shape == y.shape and (yo - y).abs().max() <= 1e-6, site["name"]
+        k = "uf_" + site["name"]
+        out[k + "_x"], out[k + "_y"], out[k + "_gy"], out[k + "_dx"] = xi, y.detach(), gyy, dx.detach()
+    # library helpers with their padding arithmetic
+    xi = torch.randn(2, 3, 8, 8, generator=g)
+    out["ufh_x"] = xi
+    out["ufh_up"] = RU.upsample2d(xi, f, impl="ref")
+    out["ufh_down"] = RU.downsample2d(xi, f, impl="ref")
+    out["ufh_filt"] = RU.filter2d(xi, f, impl="ref")
+    out["ufh_flip"] = RU.upfirdn2d(xi, RU.setup_filter([1, 2, 4]), up=[2, 1], down=[1, 2], padding=[1, 0, 2, 1],
+                                   flip_filter=True, gain=1.5, impl="ref")
+    np.savez_compressed(os.path.join(gold, "stylegan_ops.npz"), **{k: v.numpy() for k, v in out.items()})
+    print(f"[golden] stylegan_ops: {len(out)} arrays; oracle == reference impl='ref'")
+
+
 def main(ref, gold):
     knn_golden(ref, gold)
+    stylegan_ops_golden(ref, gold)
