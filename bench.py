@@ -330,11 +330,23 @@ def main():
     # ---------------- roofline of the dominant kernel from the events recorded INSIDE the timed region
     pk = peaks()
     per_kernel = {}
-    for name, flops, a, b in prof:
+    per_shape = {}
+    for name, flops, a, b, shape in prof:
+        t = a.elapsed_time(b) * 1e-3
         d = per_kernel.setdefault(name, [0.0, 0.0, 0])
         d[0] += flops
-        d[1] += a.elapsed_time(b) * 1e-3
+        d[1] += t
         d[2] += 1
+        e = per_shape.setdefault((name, shape), [0.0, 0.0, 0])
+        e[0] += flops
+        e[1] += t
+        e[2] += 1
+    if os.environ.get("ICGAN_BENCH_SHAPES"):
+        tot = sum(v[1] for v in per_shape.values())
+        print("# kernel (B,H,W,Cin,Cout,k): launches, ms total, share of TC time, TFLOP/s", file=sys.stderr)
+        for (name, shape), v in sorted(per_shape.items(), key=lambda kv: -kv[1][1])[:40]:
+            print(f"# {name:16s} {str(shape):34s} {v[2]:5d} {v[1]*1e3:9.2f} {100*v[1]/tot:5.1f}% {v[0]/v[1]*1e-12:8.1f}",
+                  file=sys.stderr)
     kinfo = {k: {"launches": v[2], "avg_ms": v[1] / v[2] * 1e3, "tflops": v[0] / v[1] * 1e-12,
                  "share_of_step": v[1] / (ms * 1e-3 * args.steps)} for k, v in per_kernel.items()}
     dom = max(per_kernel, key=lambda k: per_kernel[k][1]) if per_kernel else None

@@ -40,7 +40,7 @@ SIGNATURES = {
     "icgan_im2col_small": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_channel_sum": [vp, fp, i64, i32, i32, vp],
     "icgan_nhwc_to_cnhw": [vp, vp, i64, i32, i32, vp],
-    "icgan_sn_power_iteration": [vp, i32, i32, i32, f32, i32, vp],
+    "icgan_sn_power_iteration": [vp, i32, i32, i32, i64, f32, i32, vp],
     "icgan_sn_prepare_weight": [fp, fp, vp, vp, i32, i32, i32, i32, vp],
     "icgan_sn_weight_grad": [fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, vp],
     "icgan_bn_train_stats": [vp, i64, i32, i32, fp, fp, fp, fp, fp, f32, f32, vp],

@@ -16,6 +16,7 @@ struct GemmParams {
   float alpha, beta;
   const float* alpha_dev;
   const float* bias;
+  int splits, k_per_split;  // split-K (batch == 1, float32 C zeroed by the host, atomic accumulation)
 };
 
 template <typename TA, typename TB, typename TC>
@@ -24,7 +25,9 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ Bm, TC* __rest
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, b = blockIdx.z;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int b = p.splits > 1 ? 0 : blockIdx.z, split = p.splits > 1 ? blockIdx.z : 0;
+  const int kbeg = split * p.k_per_split, kend = p.splits > 1 ? min(p.K, kbeg + p.k_per_split) : p.K;
   const TA* Ab = A + b * p.sab;
   const TB* Bb = Bm + b * p.sbb;
   TC* Cb = C + b * p.scb;
@@ -34,13 +37,13 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ Bm, TC* __rest
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < p.K; k0 += 16) {
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + lk + j;
       const int m = m0 + lr, n = n0 + lr;
-      As[lk + j][lr] = (m < p.M && k < p.K) ? ld_as_float(Ab, m * p.sam + k * p.sak) : 0.f;
-      Bs[lk + j][lr] = (n < p.N && k < p.K) ? ld_as_float(Bb, k * p.sbk + n * p.sbn) : 0.f;
+      As[lk + j][lr] = (m < p.M && k < kend) ? ld_as_float(Ab, m * p.sam + k * p.sak) : 0.f;
+      Bs[lk + j][lr] = (n < p.N && k < kend) ? ld_as_float(Bb, k * p.sbk + n * p.sbn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -67,8 +70,12 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ Bm, TC* __rest
       const int n = n0 + tx * 4 + j;
       if (n >= p.N) continue;
       float v = alpha * acc[i][j];
-      if (p.bias) v += p.bias[n];
+      if (p.bias && split == 0) v += p.bias[n];
       const int64_t off = m * p.scm + n * p.scn;
+      if (p.splits > 1) {
+        atomicAdd(reinterpret_cast<float*>(Cb) + off, v);
+        continue;
+      }
       if (p.beta != 0.f) v = fmaf(p.beta, ld_as_float(Cb, off), v);
       st_from_float(Cb, off, v);
     }
@@ -85,9 +92,23 @@ extern "C" int icgan_gemm(const void* A, const void* B, void* C, int M, int N, i
                           int b_dtype, int c_dtype, void* stream) {
   ICGAN_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "icgan_gemm: bad arguments");
   ICGAN_REQUIRE(batch <= 65535, "icgan_gemm: batch too large");
-  GemmParams p{M, N, K, batch, sam, sak, sab, sbk, sbn, sbb, scm, scn, scb, alpha, beta, alpha_dev, bias};
-  dim3 grid(static_cast<unsigned>((N + 63) / 64), static_cast<unsigned>((M + 63) / 64), static_cast<unsigned>(batch));
+  GemmParams p{M, N, K, batch, sam, sak, sab, sbk, sbn, sbb, scm, scn, scb, alpha, beta, alpha_dev, bias, 1, K};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+  // skinny products (the [B, 657] x [C, 657]^T ccbn embeddings): too few tiles to fill 148 SMs -> split K
+  if (batch == 1 && beta == 0.f && c_dtype == ICGAN_F32 && K >= 256 && tiles < num_sms() && scn == 1 &&
+      scm == static_cast<int64_t>(N)) {
+    int splits = (2 * num_sms() + tiles - 1) / tiles;
+    if (splits > (K + 127) / 128) splits = (K + 127) / 128;
+    if (splits > 32) splits = 32;
+    if (splits > 1) {
+      p.k_per_split = ((K + splits - 1) / splits + 15) / 16 * 16;
+      p.splits = (K + p.k_per_split - 1) / p.k_per_split;
+      ICGAN_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * static_cast<size_t>(M) * N, s));
+    }
+  }
+  dim3 grid(static_cast<unsigned>((N + 63) / 64), static_cast<unsigned>((M + 63) / 64),
+            static_cast<unsigned>(p.splits > 1 ? p.splits : batch));
   typedef __nv_bfloat16 bf;
   const int key = (a_dtype == ICGAN_BF16) * 4 + (b_dtype == ICGAN_BF16) * 2 + (c_dtype == ICGAN_BF16);
   switch (key) {

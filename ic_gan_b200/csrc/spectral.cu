@@ -27,11 +27,20 @@ __global__ void sn_zero_kernel(const IcganSnLayer* layers) {
 }
 
 constexpr int kSnRowChunk = 64;
-// v_raw[k] += sum_{r in chunk} u[r] W[r][k]     grid: (col blocks, row chunks, layers)
-__global__ void sn_wt_u_kernel(const IcganSnLayer* layers) {
-  const IcganSnLayer L = layers[blockIdx.z];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r0 = blockIdx.y * kSnRowChunk;
+// v_raw[k] += sum_{r in chunk} u[r] W[r][k].  Flat grid over all (layer, column block, row chunk) work items: block b
+// finds its layer by scanning the per-layer item counts (<= a few dozen layers), so no block is launched idle.
+__global__ void sn_wt_u_kernel(const IcganSnLayer* layers, int n_layers) {
+  int item = blockIdx.x, li = 0, cbs = 0;
+  for (; li < n_layers; ++li) {
+    cbs = (layers[li].cols + 127) / 128;
+    const int items = cbs * ((layers[li].rows + kSnRowChunk - 1) / kSnRowChunk);
+    if (item < items) break;
+    item -= items;
+  }
+  if (li >= n_layers) return;
+  const IcganSnLayer L = layers[li];
+  const int k = (item % cbs) * blockDim.x + threadIdx.x;
+  const int r0 = (item / cbs) * kSnRowChunk;
   if (k >= L.cols || r0 >= L.rows) return;
   const int r1 = min(L.rows, r0 + kSnRowChunk);
   const float* w = L.W + k;
@@ -148,11 +157,11 @@ using namespace icgan;
 #define STREAM static_cast<cudaStream_t>(stream)
 
 extern "C" int icgan_sn_power_iteration(const IcganSnLayer* layers_dev, int n_layers, int max_rows, int max_cols,
-                                        float eps, int update_u, void* stream) {
-  ICGAN_REQUIRE(layers_dev && n_layers > 0 && max_rows > 0 && max_cols > 0, "icgan_sn_power_iteration: bad arguments");
+                                        int64_t wt_u_items, float eps, int update_u, void* stream) {
+  ICGAN_REQUIRE(layers_dev && n_layers > 0 && max_rows > 0 && max_cols > 0 && wt_u_items > 0,
+                "icgan_sn_power_iteration: bad arguments");
   sn_zero_kernel<<<n_layers, 256, 0, STREAM>>>(layers_dev);
-  sn_wt_u_kernel<<<dim3((max_cols + 127) / 128, (max_rows + kSnRowChunk - 1) / kSnRowChunk, n_layers), 128, 0,
-                   STREAM>>>(layers_dev);
+  sn_wt_u_kernel<<<static_cast<unsigned>(wt_u_items), 128, 0, STREAM>>>(layers_dev, n_layers);
   sn_vnorm_kernel<<<n_layers, 256, 0, STREAM>>>(layers_dev);
   sn_w_v_kernel<<<dim3((max_rows + 7) / 8, n_layers), 256, 0, STREAM>>>(layers_dev, eps);
   sn_finish_kernel<<<n_layers, 256, 0, STREAM>>>(layers_dev, eps, update_u);

@@ -30,8 +30,11 @@ def _timed(kernel: str, flops: float, fn):
     e0.record()
     out = fn()
     e1.record()
-    PROFILE.append((kernel, flops, e0, e1))
+    PROFILE.append((kernel, flops, e0, e1, _SHAPE[0]))
     return out
+
+
+_SHAPE = [None]  # set by the conv wrappers so bench.py can attribute time to layer shapes
 
 
 # ===================================================================================== spectral-norm state
@@ -175,8 +178,9 @@ def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype,
             table_cache["key"] = key
             table_cache["max_rows"] = max(s.rows for s in sn_states)
             table_cache["max_cols"] = max(s.cols for s in sn_states)
+            table_cache["items"] = sum(((s.cols + 127) // 128) * ((s.rows + 63) // 64) for s in sn_states)
         call("icgan_sn_power_iteration", ptr(table_cache["table"]), len(sn_states), table_cache["max_rows"],
-             table_cache["max_cols"], float(eps), 1 if training else 0, stream_ptr())
+             table_cache["max_cols"], table_cache["items"], float(eps), 1 if training else 0, stream_ptr())
         if training:  # sv0 is a log-only buffer (layers.py:108-111)
             with torch.no_grad():
                 torch._foreach_copy_([s.module.sv0 for s in sn_states], [s.sigma[:1] for s in sn_states])
@@ -188,6 +192,7 @@ def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype,
 # ===================================================================================== convolution
 def _tc_conv(x, wk, alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act):
     rdt = dt(residual) if residual is not None else L.F32
+    _SHAPE[0] = (B, H, W, cin, cout, k)
     _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
            lambda: call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(alpha), ptr(bias), ptr(residual), ptr(y), B, H, W, cin,
                         cout, k, dt(y), rdt, res_shift, act, stream_ptr()))
@@ -241,6 +246,7 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
 
 
 def _wgrad_tc(x, dy, G, B, H, W, cin, cout, k):
+    _SHAPE[0] = (B, H, W, cin, cout, k)
     _timed("tc_wgrad_kernel", 2.0 * B * H * W * cout * cin * k * k,
            lambda: call("icgan_conv2d_wgrad_tc", ptr(x), ptr(dy), ptr(G), B, H, W, cin, cout, k, stream_ptr()))
 

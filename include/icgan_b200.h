@@ -94,9 +94,10 @@ typedef struct {
   int rows, cols;
 } IcganSnLayer;
 
-/* One power-iteration step for n_layers layers (descriptor table in DEVICE memory). max_rows/max_cols size the grid. */
-int icgan_sn_power_iteration(const IcganSnLayer* layers_dev, int n_layers, int max_rows, int max_cols, float eps,
-                             int update_u, void* stream);
+/* One power-iteration step for n_layers layers (descriptor table in DEVICE memory). max_rows/max_cols size the
+ * row-dot grid; wt_u_items = sum over layers of ceil(cols/128)*ceil(rows/64) sizes the flat W^T u grid. */
+int icgan_sn_power_iteration(const IcganSnLayer* layers_dev, int n_layers, int max_rows, int max_cols,
+                             int64_t wt_u_items, float eps, int update_u, void* stream);
 /* W (float32 OIHW) * inv_sigma -> wk_fwd [Cout,k,k,Cin] and/or wk_dgrad [Cin,k,k,Cout] (taps flipped), out_dtype.
  * inv_sigma_dev NULL = no scaling. ksize=1 covers SNLinear/SNEmbedding ([out,in] stays [out,in]). */
 int icgan_sn_prepare_weight(const float* W, const float* inv_sigma_dev, void* wk_fwd, void* wk_dgrad, int Cout,
