@@ -66,7 +66,10 @@ def bias_act(x, b=None, dim=1, act="linear", alpha=None, gain=None, clamp=None, 
                 y = _launch(x, b, None, None, None, 0, dim, spec, alpha, gain, clamp)
             ctx.save_for_backward(x if "x" in spec.ref or spec.has_2nd_grad else None,
                                   b if "x" in spec.ref or spec.has_2nd_grad else None,
-                                  y if "y" in spec.ref else None)
+                                  # the reference's CUDA path does not save y for act='linear' and therefore ignores the
+                                  # clamp in backward (bias_act.py:236-241); its own impl='ref' (the pinned oracle) masks
+                                  # it, which is the mathematically correct derivative -- followed here.
+                                  y if ("y" in spec.ref or clamp >= 0) else None)
             ctx.has_b = b is not None
             return y
 

@@ -82,10 +82,14 @@ def test_gpu_upfirdn2d(cuda_device, gold):
             y = U.upfirdn2d(x, f, up=site["up"], down=site["down"], padding=site["padding"], gain=site["gain"])
             assert y.shape == gold[k + "_y"].shape
             assert (y.cpu() - gold[k + "_y"]).abs().max() <= 1e-5, (site["name"], layout)
-            (dx,) = torch.autograd.grad(y, x, gold[k + "_gy"].to(cuda_device), create_graph=True)
+            gy = gold[k + "_gy"].to(cuda_device).requires_grad_(True)
+            (dx,) = torch.autograd.grad(y, x, gy, create_graph=True)
             assert (dx.cpu() - gold[k + "_dx"]).abs().max() <= 1e-5, (site["name"], layout)
-            (ddy,) = torch.autograd.grad(dx.sum(), x, allow_unused=True)  # graph is differentiable again (linear op)
-            assert ddy is None or torch.isfinite(ddy).all()
+            # double backward (R1 / path length): d<dx, v>/d(gy) is the forward op applied to v
+            v = torch.randn_like(dx)
+            (ddy,) = torch.autograd.grad(dx, gy, v)
+            ref = U.upfirdn2d(v, f, up=site["up"], down=site["down"], padding=site["padding"], gain=site["gain"])
+            assert (ddy - ref).abs().max() <= 1e-5
     x = gold["ufh_x"].to(cuda_device)
     assert (U.upsample2d(x, f).cpu() - gold["ufh_up"]).abs().max() <= 1e-5
     assert (U.downsample2d(x, f).cpu() - gold["ufh_down"]).abs().max() <= 1e-5
