@@ -191,6 +191,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("ICGAN_NCCL_DEBUG", "WARN")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
