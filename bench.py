@@ -364,7 +364,8 @@ def main():
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": w["name"], "per_gpu_batch": Bg, "micro_batch": m, "accumulations": acc,
                        "global_batch": Bg * world, "parallelism": f"dp{world}", "l2": "inputs larger than L2",
-                       "optimizer": "torch.optim.Adam(fused) x2 + EMA", "step_gflop_per_image": f_step},
+                       "optimizer": "torch.optim.Adam(fused) x2 + EMA", "step_gflop_per_image": f_step,
+                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
             "roofline": roofline,
             "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks}

@@ -271,39 +271,47 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u;
-      for (int c = 0; c < p.BN; c += 16) {
+      auto emit8 = [&](const uint32_t* rr, int co) {
+        if (valid && co < p.Cout) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = alpha * __uint_as_float(rr[j]);
+          if (p.bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
+            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.res) {
+            float rv[8];
+            load8(p.res, rpix * p.Cout + co, p.res_bf16, rv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += rv[j];
+          }
+          if (p.act == ICGAN_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == ICGAN_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+          }
+          store8(p.y, pix * p.Cout + co, p.out_bf16, v);
+        }
+      };
+      int c = 0;
+      for (; c + 32 <= p.BN; c += 32) {  // 32 accumulator columns per TMEM round trip
+        uint32_t r[32];
+        tmem_ld32(taddr + static_cast<uint32_t>(c), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) emit8(r + g8 * 8, t.co0 + c + g8 * 8);
+      }
+      for (; c < p.BN; c += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + static_cast<uint32_t>(c), r);
         tmem_ld_wait();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int co = t.co0 + c + half * 8;
-          if (valid && co < p.Cout) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = alpha * __uint_as_float(r[half * 8 + j]);
-            if (p.bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.res) {
-              float rv[8];
-              load8(p.res, rpix * p.Cout + co, p.res_bf16, rv);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += rv[j];
-            }
-            if (p.act == ICGAN_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (p.act == ICGAN_ACT_TANH) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
-            }
-            store8(p.y, pix * p.Cout + co, p.out_bf16, v);
-          }
-        }
+        emit8(r, t.co0 + c);
+        emit8(r + 8, t.co0 + c + 8);
       }
       tc_fence_before();
       __syncwarp();
@@ -544,9 +552,11 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   p.tiles_w = ceil_div(W, p.TW);
   p.tiles_h = ceil_div(H, p.TH);
   const int tiles_b = ceil_div(B, p.TN);
-  p.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  // K-chunk width: 128-byte TMA rows whenever possible -- the TMA engine issues one request per box row, so 64-byte
+  // rows (cw=32) halve its byte rate; a ragged tail (e.g. Cin=96 -> 64 + 32) is zero-filled by TMA on BOTH operands.
+  p.cw = Cin >= 64 ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.swz = static_cast<uint32_t>(p.cw * 2);
-  p.chunks = Cin / p.cw;
+  p.chunks = (Cin + p.cw - 1) / p.cw;
   p.k_iters = p.taps * p.chunks;
   if (Cout <= 256) p.BN = (Cout + 15) / 16 * 16;
   else if (Cout % 256 == 0) p.BN = 256;
