@@ -31,7 +31,7 @@ class IcganSnLayer(C.Structure):
 
 # name -> argtypes (all return int). Mirrors include/icgan_b200.h one to one; tests check the two stay in sync.
 SIGNATURES = {
-    "icgan_conv2d_tc": [vp, vp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_conv2d_tc": [vp, vp, fp, fp, vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_tc": [vp, vp, fp, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_simt": [vp, fp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_simt": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
@@ -44,6 +44,7 @@ SIGNATURES = {
     "icgan_sn_prepare_weight": [fp, fp, vp, vp, i32, i32, i32, i32, vp],
     "icgan_sn_weight_grad": [fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, vp],
     "icgan_bn_train_stats": [vp, i64, i32, i32, fp, fp, fp, fp, fp, f32, f32, vp],
+    "icgan_bn_stats_from_sums": [fp, fp, i64, i32, fp, fp, fp, fp, f32, f32, vp],
     "icgan_bn_apply": [vp, vp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_bn_bwd_reduce": [vp, vp, fp, fp, fp, fp, i32, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_bn_bwd_apply": [vp, vp, vp, fp, fp, fp, fp, i32, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -85,10 +85,17 @@ class SNConv2d(nn.Conv2d, SN):
             raise NotImplementedError("SNConv2d on B200: square 1x1/3x3 kernels, stride 1, 'same' padding only")
         self._sn_init("conv", num_svs, num_itrs, out_channels, eps)
 
-    def conv_nhwc(self, x, residual=None, res_shift=0, act=ACT_NONE, out_dtype=None):
+    def conv_nhwc(self, x, residual=None, res_shift=0, act=ACT_NONE, out_dtype=None, stats=None):
         st = self._sn_ready()
         return ops.SNConvFn.apply(x, self.weight, self.bias, residual, st, res_shift, act,
-                                  out_dtype if out_dtype is not None else x.dtype)
+                                  out_dtype if out_dtype is not None else x.dtype, stats)
+
+    def bn_stats_buffer(self, x):
+        """float32 [2*Cout] accumulator if this conv can emit the batch statistics of its output from its epilogue
+        (tensor-core path, training, Cout % 32 == 0), else None."""
+        if not self.training or x.dtype != torch.bfloat16 or self.out_channels % 32 or self.in_channels % 16:
+            return None
+        return torch.zeros(2 * self.out_channels, device=x.device, dtype=torch.float32)
 
     def forward(self, x):
         xin = to_nhwc(x)
@@ -162,11 +169,11 @@ class ccbn(nn.Module):
         self.register_buffer("stored_mean", torch.zeros(output_size))
         self.register_buffer("stored_var", torch.ones(output_size))
 
-    def fused(self, x_nhwc, y, relu=False, up=False, out_dtype=None):
+    def fused(self, x_nhwc, y, relu=False, up=False, out_dtype=None, sums=None, shift=None):
         gain = 1 + self.gain(y)
         bias = self.bias(y)
         return ops.BNActFn.apply(x_nhwc, gain, bias, self.stored_mean, self.stored_var, self.training, self.eps, 0.1,
-                                 relu, up, out_dtype if out_dtype is not None else x_nhwc.dtype)
+                                 relu, up, out_dtype if out_dtype is not None else x_nhwc.dtype, sums, shift)
 
     def forward(self, x, y):
         return to_nchw(self.fused(to_nhwc(x), y))
@@ -187,10 +194,10 @@ class bn(nn.Module):
         self.gain = P(torch.ones(output_size), requires_grad=True)
         self.bias = P(torch.zeros(output_size), requires_grad=True)
 
-    def fused(self, x_nhwc, relu=False, out_dtype=None):
+    def fused(self, x_nhwc, relu=False, out_dtype=None, sums=None, shift=None):
         return ops.BNActFn.apply(x_nhwc, self.gain, self.bias, self.stored_mean, self.stored_var, self.training,
                                  self.eps, self.momentum, relu, False,
-                                 out_dtype if out_dtype is not None else x_nhwc.dtype)
+                                 out_dtype if out_dtype is not None else x_nhwc.dtype, sums, shift)
 
     def forward(self, x, y=None):
         return to_nchw(self.fused(to_nhwc(x)))
@@ -218,12 +225,20 @@ class GBlock(nn.Module):
         self.bn2 = which_bn(out_channels)
 
     def forward_nhwc(self, x, y):
+        """Batch statistics for bn2 (and for whichever batch norm consumes this block's output) are accumulated by the
+        producing conv's epilogue; they travel with the tensor as the attribute `_icgan_bn = (sums, shift)`."""
         up = bool(self.upsample)
-        h = self.bn1.fused(x, y, relu=True, up=up)
-        h = self.conv1.conv_nhwc(h)
-        h = self.bn2.fused(h, y, relu=True, up=False)
+        pre = getattr(x, "_icgan_bn", (None, None))
+        h = self.bn1.fused(x, y, relu=True, up=up, sums=pre[0], shift=pre[1])
+        s1 = self.conv1.bn_stats_buffer(h)
+        h = self.conv1.conv_nhwc(h, stats=s1)
+        h = self.bn2.fused(h, y, relu=True, up=False, sums=s1, shift=self.conv1.bias if s1 is not None else None)
         sc = self.conv_sc.conv_nhwc(x) if self.learnable_sc else x
-        return self.conv2.conv_nhwc(h, residual=sc, res_shift=1 if up else 0)
+        s2 = self.conv2.bn_stats_buffer(h)
+        out = self.conv2.conv_nhwc(h, residual=sc, res_shift=1 if up else 0, stats=s2)
+        if s2 is not None:
+            out._icgan_bn = (s2, self.conv2.bias)
+        return out
 
     def forward(self, x, y):
         return to_nchw(self.forward_nhwc(to_nhwc(x), y))

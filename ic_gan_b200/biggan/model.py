@@ -209,7 +209,8 @@ class Generator(_SNNetwork):
         for i, stage in enumerate(self.blocks):
             for block in stage:
                 h = block.forward_nhwc(h, ys[i]) if isinstance(block, layers.GBlock) else block.forward_nhwc(h)
-        h = self.output_layer[0].fused(h, relu=True)
+        pre = getattr(h, "_icgan_bn", (None, None))
+        h = self.output_layer[0].fused(h, relu=True, sums=pre[0], shift=pre[1])
         out = self.output_layer[2].conv_nhwc(h, act=ACT_TANH, out_dtype=torch.float32)
         return layers.to_nchw(out)
 

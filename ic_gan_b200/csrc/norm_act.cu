@@ -74,6 +74,24 @@ __global__ void bn_finalize_kernel(const float* __restrict__ ws, float* running_
   }
 }
 
+__global__ void bn_from_sums_kernel(const float* __restrict__ sums, const float* __restrict__ shift, float* running_mean,
+                                    float* running_var, float* __restrict__ mean, float* __restrict__ invstd, int64_t P,
+                                    int C, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invP = 1.f / static_cast<float>(P);
+  const float m0 = sums[c] * invP;                         // mean of (y - shift)
+  const float var = fmaxf(sums[C + c] * invP - m0 * m0, 0.f);  // biased variance (shift-invariant)
+  const float m = m0 + (shift ? shift[c] : 0.f);
+  mean[c] = m;
+  invstd[c] = rsqrtf(var + eps);
+  if (running_mean) {
+    const float unbiased = P > 1 ? var * (static_cast<float>(P) / static_cast<float>(P - 1)) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
 // ---------------------------------------------------------------- apply:  y = act(xhat * gain[n,c] + bias[n,c]) (+up2)
 template <typename TI, typename TO>
 __global__ void bn_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ mean,
@@ -390,6 +408,16 @@ extern "C" int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, 
   })
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(ws, running_mean, running_var, mean, invstd, P, C, eps,
                                                           momentum);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_bn_stats_from_sums(const float* sums, const float* shift, int64_t P, int C, float* running_mean,
+                                        float* running_var, float* mean, float* invstd, float eps, float momentum,
+                                        void* stream) {
+  ICGAN_REQUIRE(sums && mean && invstd && P > 0 && C > 0, "icgan_bn_stats_from_sums: bad arguments");
+  bn_from_sums_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, shift, running_mean, running_var, mean, invstd, P, C,
+                                                          eps, momentum);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -118,6 +118,7 @@ struct TcConvParams {
   const float* bias;
   const void* res;
   const float* alpha;  // device scalar multiplied into the accumulator (1/sigma of spectral norm), may be null
+  float* stats;        // optional [2*Cout]: += sum_p (y - bias), += sum_p (y - bias)^2 of the (pre-rounding) outputs
 };
 
 struct TileCoord {
@@ -149,6 +150,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* xpose = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][32][33] scratch for the BN-statistics epilogue
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -305,6 +307,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) emit8(r + g8 * 8, t.co0 + c + g8 * 8);
+        if (p.stats) {
+          // batch-norm statistics of this 32-pixel x 32-channel block: transpose through smem, one channel per lane.
+          // Values are centred on the bias (y - bias = alpha*acc [+ residual]) to keep E[x^2]-E[x]^2 well conditioned.
+          float* xp = xpose + (warp - 2) * (32 * 33);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = 0.f;
+            if (valid && t.co0 + c + j < p.Cout) {
+              v = alpha * __uint_as_float(r[j]);
+              if (p.res) v += p.res_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.res)[rpix * p.Cout + t.co0 + c + j])
+                                         : static_cast<const float*>(p.res)[rpix * p.Cout + t.co0 + c + j];
+            }
+            xp[lane * 33 + j] = v;
+          }
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const float v = xp[rr * 33 + lane];
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+          }
+          const int co = t.co0 + c + lane;
+          if (co < p.Cout) {
+            atomicAdd(p.stats + co, s1);
+            atomicAdd(p.stats + p.Cout + co, s2);
+          }
+          __syncwarp();
+        }
       }
       for (; c < p.BN; c += 16) {
         uint32_t r[16];
@@ -534,8 +565,8 @@ __global__ void nhwc_to_cnhw_kernel(const T* __restrict__ x, __nv_bfloat16* __re
 using namespace icgan;
 
 extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha_dev, const float* bias,
-                               const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize,
-                               int out_dtype, int res_dtype, int res_shift, int act, void* stream) {
+                               const void* residual, void* y, float* bn_stats, int B, int H, int W, int Cin, int Cout,
+                               int ksize, int out_dtype, int res_dtype, int res_shift, int act, void* stream) {
   ICGAN_REQUIRE(x && wk && y, "icgan_conv2d_tc: null pointer");
   ICGAN_REQUIRE(ksize == 1 || ksize == 3, "icgan_conv2d_tc: ksize must be 1 or 3 (got %d)", ksize);
   ICGAN_REQUIRE(B > 0 && H > 0 && W > 0, "icgan_conv2d_tc: bad shape B=%d H=%d W=%d", B, H, W);
@@ -552,11 +583,11 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   p.tiles_w = ceil_div(W, p.TW);
   p.tiles_h = ceil_div(H, p.TH);
   const int tiles_b = ceil_div(B, p.TN);
-  // K-chunk width: 128-byte TMA rows whenever possible -- the TMA engine issues one request per box row, so 64-byte
-  // rows (cw=32) halve its byte rate; a ragged tail (e.g. Cin=96 -> 64 + 32) is zero-filled by TMA on BOTH operands.
-  p.cw = Cin >= 64 ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  // K-chunk width = largest of 64/32/16 dividing Cin. (Measured: padding Cin=96 to 2x64 with TMA zero-fill is SLOWER,
+  // 481 -> 392 TFLOP/s: the kernel is bound by bytes staged L2 -> smem, and padding stages 33% more.)
+  p.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.swz = static_cast<uint32_t>(p.cw * 2);
-  p.chunks = (Cin + p.cw - 1) / p.cw;
+  p.chunks = Cin / p.cw;
   p.k_iters = p.taps * p.chunks;
   if (Cout <= 256) p.BN = (Cout + 15) / 16 * 16;
   else if (Cout % 256 == 0) p.BN = 256;
@@ -576,7 +607,7 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   p.G = G;
   p.n_stage_iters = (p.k_iters + G - 1) / G;
   p.stage_bytes = static_cast<uint32_t>(G) * chunk_bytes;
-  const uint32_t tail = 1024u /*align slack*/ + 512u /*barriers*/;
+  const uint32_t tail = 1024u /*align slack*/ + 512u /*barriers*/ + 4u * 32u * 33u * 4u /*stats transpose*/;
   int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   ICGAN_REQUIRE(stages >= 2, "icgan_conv2d_tc: tile does not fit shared memory");
@@ -586,7 +617,9 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   p.res_bf16 = res_dtype == ICGAN_BF16;
   p.res_shift = res_shift;
   p.act = act;
-  p.y = y; p.bias = bias; p.res = residual; p.alpha = alpha_dev;
+  p.y = y; p.bias = bias; p.res = residual; p.alpha = alpha_dev; p.stats = bn_stats;
+  ICGAN_REQUIRE(!bn_stats || (act == ICGAN_ACT_NONE && Cout % 32 == 0),
+                "icgan_conv2d_tc: bn_stats needs act=none and Cout a multiple of 32 (got %d)", Cout);
 
   CUtensorMap tmA, tmB;
   {

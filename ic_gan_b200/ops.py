@@ -190,12 +190,12 @@ def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype,
 
 
 # ===================================================================================== convolution
-def _tc_conv(x, wk, alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act):
+def _tc_conv(x, wk, alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act, stats=None):
     rdt = dt(residual) if residual is not None else L.F32
     _SHAPE[0] = (B, H, W, cin, cout, k)
     _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
-           lambda: call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(alpha), ptr(bias), ptr(residual), ptr(y), B, H, W, cin,
-                        cout, k, dt(y), rdt, res_shift, act, stream_ptr()))
+           lambda: call("icgan_conv2d_tc", ptr(x), ptr(wk), ptr(alpha), ptr(bias), ptr(residual), ptr(y), ptr(stats), B,
+                        H, W, cin, cout, k, dt(y), rdt, res_shift, act, stream_ptr()))
 
 
 def _im2col(x: Tensor, k: int, kp: int) -> Tensor:
@@ -206,15 +206,17 @@ def _im2col(x: Tensor, k: int, kp: int) -> Tensor:
 
 
 def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: int, out_dtype, dgrad: bool = False,
-                  keep: Optional[dict] = None):
+                  keep: Optional[dict] = None, stats: Optional[Tensor] = None):
     """act(alpha * conv(x, operand) + bias + residual); `keep` receives tensors worth saving for the backward."""
     B, H, W, cin = x.shape
     wk, mode, kp = (st.wk_fwd, st.mode, st.kp) if not dgrad else (st.wk_dgrad, st.mode_d, st.kp_d)
     w = st.module.weight
     cout, k = (w.shape[0], w.shape[2]) if not dgrad else (w.shape[1], w.shape[2])
+    if stats is not None and mode != "tc":
+        raise RuntimeError("fused batch-norm statistics need the tensor-core conv path")
     if mode == "tc":
         y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
-        _tc_conv(x, wk, st.alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act)
+        _tc_conv(x, wk, st.alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act, stats)
         return y
     if mode == "col":  # RGB-side input: im2col (27 -> 32 columns) + tensor-core 1x1
         xcol = _im2col(x, k, kp)
@@ -257,10 +259,10 @@ class SNConvFn(torch.autograd.Function):
     using conv1x1(up(x)) == up(conv1x1(x))."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, st: SNState, res_shift: int, act: int, out_dtype):
+    def forward(ctx, x, weight, bias, residual, st: SNState, res_shift: int, act: int, out_dtype, stats=None):
         x = x.contiguous()
         keep = {}
-        y = _conv_forward(x, st, bias, residual, res_shift, act, out_dtype, keep=keep)
+        y = _conv_forward(x, st, bias, residual, res_shift, act, out_dtype, keep=keep, stats=stats)
         ctx.st, ctx.res_shift, ctx.act = st, res_shift, act
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.res_dtype = residual.dtype if residual is not None else None
@@ -322,7 +324,7 @@ class SNConvFn(torch.autograd.Function):
                     call("icgan_conv2d_wgrad_simt", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, 1, k // 2, dt(x),
                          stream_ptr())
             dW = st.weight_grad(G)
-        return dx, dW, db, dres, None, None, None, None
+        return dx, dW, db, dres, None, None, None, None, None
 
 
 # ===================================================================================== linear / embedding
@@ -393,14 +395,19 @@ class BNActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gain, bias, running_mean, running_var, training: bool, eps: float, momentum: float, relu: bool,
-                up: bool, out_dtype):
+                up: bool, out_dtype, sums=None, shift=None):
         x = x.contiguous()
         B, H, W, Cc = x.shape
         gain = gain.contiguous().float()
         bias = bias.contiguous().float()
         gstride = Cc if gain.dim() == 2 else 0
         dev = x.device
-        if training:
+        if training and sums is not None:  # statistics already accumulated by the producing conv's epilogue
+            mean = torch.empty(Cc, device=dev, dtype=torch.float32)
+            invstd = torch.empty(Cc, device=dev, dtype=torch.float32)
+            call("icgan_bn_stats_from_sums", ptr(sums), ptr(shift), B * H * W, Cc, ptr(running_mean), ptr(running_var),
+                 ptr(mean), ptr(invstd), float(eps), float(momentum), stream_ptr())
+        elif training:
             ws = torch.empty(2 * Cc, device=dev, dtype=torch.float32)
             mean = torch.empty(Cc, device=dev, dtype=torch.float32)
             invstd = torch.empty(Cc, device=dev, dtype=torch.float32)
@@ -446,7 +453,7 @@ class BNActFn(torch.autograd.Function):
                  ptr(m1), ptr(m2), B, H, W, Cc, int(relu), int(up), dt(x), dt(dy), stream_ptr())
             if dx.dtype != x.dtype:
                 dx = dx.to(x.dtype)
-        return dx, dgain, dbias, None, None, None, None, None, None, None, None
+        return dx, dgain, dbias, None, None, None, None, None, None, None, None, None, None
 
 
 # ===================================================================================== small NHWC ops

@@ -43,10 +43,13 @@ int icgan_version(void);
  * out_dtype/res_dtype: ICGAN_F32|ICGAN_BF16. residual may be NULL; res_shift=1 reads residual[n,h/2,w/2,co] from a
  * half-resolution tensor (the nearest-upsampled shortcut of GBlock, layers.py:545-552). bias may be NULL.
  * alpha_dev (device scalar, may be NULL): the accumulator is scaled by it before bias -- 1/sigma of SN.W_ (layers.py:112).
+ * bn_stats (may be NULL; needs act none, Cout%32==0): float32 [2*Cout], ACCUMULATES sum and sum of squares over all output
+ * pixels of (y - bias), i.e. the batch statistics the following ccbn/bn needs (layers.py:412-421), from the fp32
+ * accumulators -- saves the two statistics passes over the activation (see icgan_bn_stats_from_sums).
  * Serves forward, and dgrad when called with the flipped/transposed weight copy. */
 int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha_dev, const float* bias, const void* residual,
-                    void* y, int B, int H, int W, int Cin, int Cout, int ksize, int out_dtype, int res_dtype,
-                    int res_shift, int act, void* stream);
+                    void* y, float* bn_stats, int B, int H, int W, int Cin, int Cout, int ksize, int out_dtype,
+                    int res_dtype, int res_shift, int act, void* stream);
 
 /* Tensor-core weight gradient for 3x3/1x1 stride-1 convs (replaces cudnn_convolution_backward_weight,
  * stylegan2_ada_pytorch/torch_utils/ops/conv2d_gradfix.py:223-227, and ATen's conv backward under BigGAN):
@@ -114,6 +117,10 @@ int icgan_sn_weight_grad(const float* G_k, const float* W, const float* u_new, c
  * NULL) updated with momentum and the UNBIASED variance as F.batch_norm does. ws: 2*C floats of workspace. */
 int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, float* ws, float* running_mean,
                          float* running_var, float* mean, float* invstd, float eps, float momentum, void* stream);
+/* mean/invstd (+ running-stat update) from the shifted sums a conv epilogue accumulated: sums = [sum(y-shift) | sum((y-shift)^2)],
+ * shift = the conv bias (NULL = 0). Same outputs as icgan_bn_train_stats. */
+int icgan_bn_stats_from_sums(const float* sums, const float* shift, int64_t P, int C, float* running_mean,
+                             float* running_var, float* mean, float* invstd, float eps, float momentum, void* stream);
 /* y = act(((x-mean)*invstd) * gain[n,c] + bias[n,c]); gain/bias row stride gain_stride (0 = shared [C] vectors);
  * relu: fuse ReLU; up: write the nearest-upsampled x2 tensor [B,2H,2W,C] (GBlock, layers.py:543-546). */
 int icgan_bn_apply(const void* x, void* y, const float* mean, const float* invstd, const float* gain,

@@ -13,8 +13,13 @@ for r in csv.DictReader(lines):
     val = float(r["Metric Value"].replace(",", ""))
     unit = r.get("Metric Unit", "ns")
     scale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3, "s": 1e6}.get(unit, 1e-3)
-    name = re.sub(r"\(.*", "", r["Kernel Name"])
-    name = re.sub(r"<.*", "", name)
+    name = r["Kernel Name"]
+    name = name.replace("(anonymous namespace)::", "")
+    name = re.sub(r"\(.*", "", name)          # drop the argument list
+    name = re.sub(r"^void ", "", name)
+    base = re.sub(r"<.*", "", name)           # drop template arguments ...
+    targs = re.findall(r"<(.*)>", name)
+    name = base + ("<" + targs[0][:28] + ">" if targs else "")  # ... but keep a short hint of them
     rows.append((name, val * scale))
 tot = sum(t for _, t in rows)
 agg = defaultdict(lambda: [0, 0.0])

@@ -57,7 +57,7 @@ static int run_conv_case(const ConvCase& c, bool time_it) {
   CK(cudaMemset(dy, 0xFF, ny * 4));
   if (nr) { CK(cudaMalloc(&dr, nr * 4)); CK(cudaMemcpy(dr, hres.data(), nr * 4, cudaMemcpyHostToDevice)); }
 
-  int rc = icgan_conv2d_tc(dx, dw, nullptr, c.bias ? db : nullptr, dr, dy, c.B, c.H, c.W, c.Cin, c.Cout, c.k,
+  int rc = icgan_conv2d_tc(dx, dw, nullptr, c.bias ? db : nullptr, dr, dy, nullptr, c.B, c.H, c.W, c.Cin, c.Cout, c.k,
                            c.out_bf16 ? ICGAN_BF16 : ICGAN_F32, ICGAN_F32, c.res_mode == 2, c.act, nullptr);
   if (rc) { printf("[%s] launch error %d: %s\n", c.name, rc, icgan_last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
@@ -115,11 +115,11 @@ static int run_conv_case(const ConvCase& c, bool time_it) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 3; ++i)
-      icgan_conv2d_tc(dx, dw, nullptr, db, nullptr, dy, c.B, c.H, c.W, c.Cin, c.Cout, c.k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
+      icgan_conv2d_tc(dx, dw, nullptr, db, nullptr, dy, nullptr, c.B, c.H, c.W, c.Cin, c.Cout, c.k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
     CK(cudaEventRecord(e0));
     const int iters = 10;
     for (int i = 0; i < iters; ++i)
-      icgan_conv2d_tc(dx, dw, nullptr, db, nullptr, dy, c.B, c.H, c.W, c.Cin, c.Cout, c.k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
+      icgan_conv2d_tc(dx, dw, nullptr, db, nullptr, dy, nullptr, c.B, c.H, c.W, c.Cin, c.Cout, c.k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -226,12 +226,12 @@ static void run_prof() {
   CK(cudaMemset(x, 0x3c, nx * 2)); CK(cudaMemset(y, 0x3c, ny * 2)); CK(cudaMemset(w, 0x3c, nw * 2));
   CK(cudaMemset(dw, 0, nw * 4));
   for (int i = 0; i < 3; ++i) {
-    icgan_conv2d_tc(x, w, nullptr, nullptr, nullptr, y, B, H, W, Ci, Co, k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
+    icgan_conv2d_tc(x, w, nullptr, nullptr, nullptr, y, nullptr, B, H, W, Ci, Co, k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
     icgan_conv2d_wgrad_tc(x, y, dw, B, H, W, Ci, Co, k, nullptr);
   }
   // the 96-channel 256x256 layer (HBM/overhead-bound regime)
   for (int i = 0; i < 2; ++i) {
-    icgan_conv2d_tc(x, w, nullptr, nullptr, nullptr, y, 8, 256, 256, 96, 96, k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
+    icgan_conv2d_tc(x, w, nullptr, nullptr, nullptr, y, nullptr, 8, 256, 256, 96, 96, k, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
     icgan_conv2d_wgrad_tc(x, y, dw, 8, 256, 256, 96, 96, k, nullptr);
   }
   CK(cudaDeviceSynchronize());
