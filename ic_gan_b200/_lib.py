@@ -43,7 +43,7 @@ SIGNATURES = {
     "icgan_sn_power_iteration": [vp, i32, i32, i32, i64, f32, i32, vp],
     "icgan_sn_prepare_weight": [fp, fp, vp, vp, i32, i32, i32, i32, vp],
     "icgan_sn_weight_grad": [fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, vp],
-    "icgan_bn_train_stats": [vp, i64, i32, i32, fp, fp, fp, fp, fp, f32, f32, vp],
+    "icgan_bn_train_stats": [vp, i64, i32, i32, fp, fp, fp, fp, fp, fp, f32, f32, vp],
     "icgan_bn_stats_from_sums": [fp, fp, i64, i32, fp, fp, fp, fp, f32, f32, vp],
     "icgan_bn_apply": [vp, vp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_bn_bwd_reduce": [vp, vp, fp, fp, fp, fp, i32, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
@@ -97,7 +97,7 @@ def last_error() -> str:
 
 
 # kernels launched per entry point (everything else launches exactly one); bench.py reports the running total
-KERNELS_PER_CALL = {"icgan_bn_train_stats": 3, "icgan_sn_power_iteration": 5, "icgan_sn_weight_grad": 2, "icgan_knn_exact_row": 2}
+KERNELS_PER_CALL = {"icgan_bn_train_stats": 2, "icgan_sn_power_iteration": 5, "icgan_sn_weight_grad": 2, "icgan_knn_exact_row": 2}
 LAUNCHES = 0
 
 

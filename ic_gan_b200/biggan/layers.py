@@ -93,7 +93,8 @@ class SNConv2d(nn.Conv2d, SN):
     def bn_stats_buffer(self, x):
         """float32 [2*Cout] accumulator if this conv can emit the batch statistics of its output from its epilogue
         (tensor-core path, training, Cout % 32 == 0), else None."""
-        if not self.training or x.dtype != torch.bfloat16 or self.out_channels % 32 or self.in_channels % 16:
+        if not ops.FUSE_BN_STATS or not self.training or x.dtype != torch.bfloat16 or self.out_channels % 32 \
+                or self.in_channels % 16:
             return None
         return torch.zeros(2 * self.out_channels, device=x.device, dtype=torch.float32)
 
@@ -168,12 +169,14 @@ class ccbn(nn.Module):
         self.cross_replica, self.mybn, self.norm_style = cross_replica, mybn, norm_style
         self.register_buffer("stored_mean", torch.zeros(output_size))
         self.register_buffer("stored_var", torch.ones(output_size))
+        self._stat_hint = {}  # last batch mean (device tensor): centres the one-pass bf16 moment kernel
 
     def fused(self, x_nhwc, y, relu=False, up=False, out_dtype=None, sums=None, shift=None):
         gain = 1 + self.gain(y)
         bias = self.bias(y)
         return ops.BNActFn.apply(x_nhwc, gain, bias, self.stored_mean, self.stored_var, self.training, self.eps, 0.1,
-                                 relu, up, out_dtype if out_dtype is not None else x_nhwc.dtype, sums, shift)
+                                 relu, up, out_dtype if out_dtype is not None else x_nhwc.dtype, sums, shift,
+                                 self._stat_hint)
 
     def forward(self, x, y):
         return to_nchw(self.fused(to_nhwc(x), y))
@@ -193,11 +196,12 @@ class bn(nn.Module):
         self.register_buffer("stored_var", torch.ones(output_size))
         self.gain = P(torch.ones(output_size), requires_grad=True)
         self.bias = P(torch.zeros(output_size), requires_grad=True)
+        self._stat_hint = {}
 
     def fused(self, x_nhwc, relu=False, out_dtype=None, sums=None, shift=None):
         return ops.BNActFn.apply(x_nhwc, self.gain, self.bias, self.stored_mean, self.stored_var, self.training,
                                  self.eps, self.momentum, relu, False,
-                                 out_dtype if out_dtype is not None else x_nhwc.dtype, sums, shift)
+                                 out_dtype if out_dtype is not None else x_nhwc.dtype, sums, shift, self._stat_hint)
 
     def forward(self, x, y=None):
         return to_nchw(self.fused(to_nhwc(x)))

@@ -378,9 +378,9 @@ using namespace icgan;
 
 static int reduce_threads(int C) { return C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32)); }
 
-extern "C" int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, float* ws, float* running_mean,
-                                    float* running_var, float* mean, float* invstd, float eps, float momentum,
-                                    void* stream) {
+extern "C" int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, float* ws, const float* shift,
+                                    float* running_mean, float* running_var, float* mean, float* invstd, float eps,
+                                    float momentum, void* stream) {
   ICGAN_REQUIRE(x && ws && mean && invstd && P > 0 && C > 0, "icgan_bn_train_stats: bad arguments");
   ICGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, STREAM));
   if (dtype == ICGAN_BF16 && vec::ok(C)) {
@@ -389,10 +389,10 @@ extern "C" int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, 
     const int64_t ppb = (P + blocks - 1) / blocks;
     blocks = (P + ppb - 1) / ppb;
     const vec::bf16* xb = static_cast<const vec::bf16*>(x);
-    vec::colsum_vec_kernel<1><<<static_cast<unsigned>(blocks), vec::kThreads, 0, STREAM>>>(xb, ws, P, C, ppb);
-    vec::colsum_vec_kernel<2><<<static_cast<unsigned>(blocks), vec::kThreads, 0, STREAM>>>(xb, ws, P, C, ppb);
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(ws, running_mean, running_var, mean, invstd, P, C, eps,
-                                                            momentum);
+    // one pass over the activation: shifted first and second moments (shift = last step's batch mean, or NULL)
+    vec::shifted_moments_vec_kernel<<<static_cast<unsigned>(blocks), vec::kThreads, 0, STREAM>>>(xb, shift, ws, P, C, ppb);
+    bn_from_sums_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(ws, shift, running_mean, running_var, mean, invstd, P, C,
+                                                            eps, momentum);
     ICGAN_LAUNCH_CHECK();
     return 0;
   }

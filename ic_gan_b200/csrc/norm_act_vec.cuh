@@ -59,6 +59,36 @@ __device__ __forceinline__ void block_reduce_atomic(float (&acc)[NA][8], float* 
   }
 }
 
+// ---- single pass: ws[c] += sum (x - shift_c), ws[C+c] += sum (x - shift_c)^2   (shift ~ the channel mean keeps
+//      E[d^2] - E[d]^2 well conditioned in float32; NULL = 0)
+__global__ void __launch_bounds__(kThreads)
+shifted_moments_vec_kernel(const bf16* __restrict__ x, const float* __restrict__ shift, float* __restrict__ ws,
+                           int64_t P, int C, int64_t pix_per_block) {
+  const int CG = C >> 3, PY = kThreads / CG;
+  const int cg = threadIdx.x % CG, py = threadIdx.x / CG;
+  const bool active = py < PY;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < P ? p0 + pix_per_block : P;
+  float acc[2][8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = sh[i] = 0.f;
+  if (shift) ldf8(shift + cg * 8, sh);
+  if (active) {
+    for (int64_t p = p0 + py; p < p1; p += PY) {
+      float v[8];
+      ld8(x + p * C + cg * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[i] - sh[i];
+        acc[0][i] += d;
+        acc[1][i] = fmaf(d, d, acc[1][i]);
+      }
+    }
+  }
+  float* const dst[2] = {ws, ws + C};
+  block_reduce_atomic<2>(acc, dst, cg * 8, cg, py, CG, PY, active);
+}
+
 // ---- column sums / centred squares over [P][C]:  PASS 1: ws[c] += sum x ; PASS 2: ws[C+c] += sum (x-mean)^2 ;
 //      PASS 0: out[c] += sum x (bias gradients)
 template <int PASS>

@@ -21,6 +21,10 @@ Tensor = torch.Tensor
 # When bench.py sets PROFILE to a list, every tensor-core conv launch is bracketed by CUDA events on the launching
 # stream and recorded as (kernel, algorithmic FLOPs, start, end) — the live source of the roofline numbers.
 PROFILE = None
+# Accumulating batch-norm statistics in the producing conv's epilogue is implemented (icgan_conv2d_tc bn_stats) but OFF by
+# default: measured on B200 it lowers the conv kernels more (730 -> 654 TFLOP/s average, they are epilogue/L2-bound at
+# high resolution) than the two saved statistics passes gain.
+FUSE_BN_STATS = False
 
 
 def _timed(kernel: str, flops: float, fn):
@@ -395,7 +399,7 @@ class BNActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gain, bias, running_mean, running_var, training: bool, eps: float, momentum: float, relu: bool,
-                up: bool, out_dtype, sums=None, shift=None):
+                up: bool, out_dtype, sums=None, shift=None, hint=None):
         x = x.contiguous()
         B, H, W, Cc = x.shape
         gain = gain.contiguous().float()
@@ -411,8 +415,11 @@ class BNActFn(torch.autograd.Function):
             ws = torch.empty(2 * Cc, device=dev, dtype=torch.float32)
             mean = torch.empty(Cc, device=dev, dtype=torch.float32)
             invstd = torch.empty(Cc, device=dev, dtype=torch.float32)
-            call("icgan_bn_train_stats", ptr(x), B * H * W, Cc, dt(x), ptr(ws), ptr(running_mean), ptr(running_var),
-                 ptr(mean), ptr(invstd), float(eps), float(momentum), stream_ptr())
+            prev = hint.get("mean") if hint is not None else None  # last step's batch mean centres the one-pass moments
+            call("icgan_bn_train_stats", ptr(x), B * H * W, Cc, dt(x), ptr(ws), ptr(prev), ptr(running_mean),
+                 ptr(running_var), ptr(mean), ptr(invstd), float(eps), float(momentum), stream_ptr())
+            if hint is not None:
+                hint["mean"] = mean
         else:
             mean = running_mean.float()
             invstd = torch.rsqrt(running_var.float() + eps)
@@ -453,7 +460,7 @@ class BNActFn(torch.autograd.Function):
                  ptr(m1), ptr(m2), B, H, W, Cc, int(relu), int(up), dt(x), dt(dy), stream_ptr())
             if dx.dtype != x.dtype:
                 dx = dx.to(x.dtype)
-        return dx, dgain, dbias, None, None, None, None, None, None, None, None, None, None
+        return dx, dgain, dbias, None, None, None, None, None, None, None, None, None, None, None
 
 
 # ===================================================================================== small NHWC ops

@@ -113,10 +113,13 @@ int icgan_sn_weight_grad(const float* G_k, const float* W, const float* u_new, c
 /* ------------------------------------------------------------------------------------------------
  * Batch norm with per-sample affine (layers.ccbn, layers.py:398-437; layers.bn :485-503), NHWC.
  * ---------------------------------------------------------------------------------------------- */
-/* Two-pass batch statistics over P = B*H*W pixels: mean, invstd = rsqrt(biased var + eps); running buffers (may be
- * NULL) updated with momentum and the UNBIASED variance as F.batch_norm does. ws: 2*C floats of workspace. */
-int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, float* ws, float* running_mean,
-                         float* running_var, float* mean, float* invstd, float eps, float momentum, void* stream);
+/* Batch statistics over P = B*H*W pixels: mean, invstd = rsqrt(biased var + eps); running buffers (may be NULL)
+ * updated with momentum and the UNBIASED variance as F.batch_norm does. ws: 2*C floats of workspace. float32 input:
+ * exact two-pass (mean, then centred squares); bf16 input: ONE pass of moments shifted by shift[c] (NULL = 0; pass the
+ * previous step's batch mean to keep E[d^2]-E[d]^2 well conditioned). */
+int icgan_bn_train_stats(const void* x, int64_t P, int C, int dtype, float* ws, const float* shift,
+                         float* running_mean, float* running_var, float* mean, float* invstd, float eps,
+                         float momentum, void* stream);
 /* mean/invstd (+ running-stat update) from the shifted sums a conv epilogue accumulated: sums = [sum(y-shift) | sum((y-shift)^2)],
  * shift = the conv bias (NULL = 0). Same outputs as icgan_bn_train_stats. */
 int icgan_bn_stats_from_sums(const float* sums, const float* shift, int64_t P, int C, float* running_mean,
