@@ -115,6 +115,60 @@ def stylegan_ops_golden(ref, gold):
     print(f"[golden] stylegan_ops: {len(out)} arrays; oracle == reference impl='ref'")
 
 
+def stylegan_conv_golden(ref, gold):
+    """conv2d_resample / modulated_conv2d of the live reference (CPU), incl. first- and second-order gradients."""
+    import torch
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import stylegan_ops_oracle as S
+    sys.path.insert(0, os.path.join(ref, "stylegan2_ada_pytorch"))
+    from torch_utils.ops import conv2d_resample as RC, upfirdn2d as RU
+    from training.networks import modulated_conv2d as Rmod
+    f = RU.setup_filter([1, 3, 3, 1])
+    g = torch.Generator().manual_seed(29)
+    out = {"f": f}
+    for name, ci, co, k, up, down, pad, hw in S.CONV_SITES:
+        x = torch.randn(2, ci, hw, hw, generator=g)
+        w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = RC.conv2d_resample(xr, wr, f=f, up=up, down=down, padding=pad)
+        gy = torch.randn(y.shape, generator=g)
+        dx, dw = torch.autograd.grad(y, [xr, wr], gy, create_graph=True)
+        v = torch.randn(dx.shape, generator=g)
+        (ddw,) = torch.autograd.grad(dx, wr, v)  # second order: d<dx, v>/dw  (R1-style)
+        yo = S.conv2d_resample(x, w, f, up=up, down=down, padding=pad)
+        assert yo.shape == y.shape and (yo - y).abs().max() <= 2e-5, name
+        k_ = "cr_" + name
+        out.update({k_ + "_x": x, k_ + "_w": w, k_ + "_y": y.detach(), k_ + "_gy": gy, k_ + "_dx": dx.detach(),
+                    k_ + "_dw": dw.detach(), k_ + "_v": v, k_ + "_ddw": ddw.detach()})
+    # modulated conv: training (non-fused) and inference (fused) forms, with the gradients the loss terms need
+    for name, up, pad, k in (("mod_plain", 1, 1, 3), ("mod_up", 2, 1, 3), ("mod_rgb", 1, 0, 1)):
+        ci, co, hw = 8, 6, 8
+        x = torch.randn(3, ci, hw, hw, generator=g)
+        w = torch.randn(co, ci, k, k, generator=g)
+        st = torch.randn(3, ci, generator=g) + 1.0
+        ohw = hw * up
+        noise = torch.randn(3, 1, ohw, ohw, generator=g) * 0.1
+        dem = name != "mod_rgb"
+        xr, wr, sr = x.clone().requires_grad_(True), w.clone().requires_grad_(True), st.clone().requires_grad_(True)
+        y = Rmod(xr, wr, sr, noise=noise if dem else None, up=up, padding=pad, resample_filter=f, demodulate=dem,
+                 fused_modconv=False)
+        yf = Rmod(x, w, st, noise=noise if dem else None, up=up, padding=pad, resample_filter=f, demodulate=dem,
+                  fused_modconv=True)
+        assert (y - yf).abs().max() <= 2e-5
+        gy = torch.randn(y.shape, generator=g)
+        dx, dw, ds = torch.autograd.grad(y, [xr, wr, sr], gy, create_graph=True)
+        (dds,) = torch.autograd.grad(dx.square().sum(), sr)  # path-length style second-order term
+        yo = S.modulated_conv2d(x, w, st, noise if dem else None, up=up, padding=pad, resample_filter=f, demodulate=dem)
+        assert (yo - y).abs().max() <= 5e-5, name
+        out.update({name + "_x": x, name + "_w": w, name + "_s": st, name + "_noise": noise, name + "_y": y.detach(),
+                    name + "_gy": gy, name + "_dx": dx.detach(), name + "_dw": dw.detach(), name + "_ds": ds.detach(),
+                    name + "_dds": dds.detach()})
+    np.savez_compressed(os.path.join(gold, "stylegan_conv.npz"), **{k: v.numpy() for k, v in out.items()})
+    print(f"[golden] stylegan_conv: {len(out)} arrays; oracle == reference")
+
+
 def main(ref, gold):
     knn_golden(ref, gold)
     stylegan_ops_golden(ref, gold)
+    stylegan_conv_golden(ref, gold)

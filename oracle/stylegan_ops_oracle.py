@@ -85,3 +85,51 @@ UPFIRDN_SITES = [
     dict(name="D_skip_down", up=1, down=2, padding=[1, 1, 1, 1], gain=1.0, odd=False),
     dict(name="D_before_stride2_conv", up=1, down=1, padding=[2, 2, 2, 2], gain=1.0, odd=False),
 ]
+
+
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, flip_weight=True):
+    """The reference's generic fallback path (conv2d_resample.py:204-216): FIR-upsample, convolve, FIR-downsample. Its
+    specialised fast paths (strided / transposed convolutions) are algebraically identical to this definition."""
+    fw = fh = 1 if f is None else int(f.shape[-1])
+    if isinstance(padding, int):
+        padding = [padding] * 4
+    if len(padding) == 2:
+        padding = [padding[0], padding[0], padding[1], padding[1]]
+    px0, px1, py0, py1 = padding
+    if up > 1:
+        px0 += (fw + up - 1) // 2
+        px1 += (fw - up) // 2
+        py0 += (fh + up - 1) // 2
+        py1 += (fh - up) // 2
+    if down > 1:
+        px0 += (fw - down + 1) // 2
+        px1 += (fw - down) // 2
+        py0 += (fh - down + 1) // 2
+        py1 += (fh - down) // 2
+    x = upfirdn2d(x, f if up > 1 else None, up=up, padding=[px0, px1, py0, py1], gain=up ** 2)
+    x = F.conv2d(x, w if flip_weight else w.flip([2, 3]))
+    if down > 1:
+        x = upfirdn2d(x, f, down=down)
+    return x
+
+
+def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True):
+    """networks.py:37-117 in its mathematical form: per-sample weights w_n = W * s_n, demodulated, one conv per sample."""
+    outs = []
+    for n in range(x.shape[0]):
+        w = weight * styles[n].reshape(1, -1, 1, 1)
+        if demodulate:
+            w = w * (w.square().sum(dim=[1, 2, 3], keepdim=True) + 1e-8).rsqrt()
+        outs.append(conv2d_resample(x[n:n + 1], w, resample_filter, up=up, down=down, padding=padding))
+    y = torch.cat(outs, 0)
+    return y if noise is None else y + noise
+
+
+CONV_SITES = [  # (name, Cin, Cout, k, up, down, padding, H)
+    ("plain3", 8, 6, 3, 1, 1, 1, 8),
+    ("up3", 8, 6, 3, 2, 1, 1, 8),
+    ("down3", 8, 6, 3, 1, 2, 1, 8),
+    ("down1_skip", 8, 6, 1, 1, 2, 0, 8),
+    ("torgb1", 8, 3, 1, 1, 1, 0, 8),
+    ("up1", 8, 6, 1, 2, 1, 0, 8),
+]
