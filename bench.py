@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 # forward GFLOP per image (conv + linear + attention bmm, 2*MAC) measured on the reference modules: SURVEY.md §8(d)
 WORKLOADS = {
     "cc256": dict(name="cc-IC-GAN BigGAN 256x256 (ch96, attn@64, class+instance cond)", resolution=256, ch=96,
-                  attn="64", class_cond=True, G_f=146.43, D_f=74.67, per_gpu_batch=256, micro_batch=32),
+                  attn="64", class_cond=True, G_f=146.43, D_f=74.67, per_gpu_batch=256, micro_batch=128),
     "ic128": dict(name="IC-GAN BigGAN 128x128 (ch96, attn@64, instance cond)", resolution=128, ch=96, attn="64",
                   class_cond=False, G_f=42.26, D_f=21.68, per_gpu_batch=256, micro_batch=64),
     "ic64": dict(name="IC-GAN BigGAN 64x64 (ch64, attn@32, instance cond)", resolution=64, ch=64, attn="32",

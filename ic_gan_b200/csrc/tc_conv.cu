@@ -13,6 +13,7 @@
 //                     directly from the NHWC tensors), all 9 tap accumulators resident in TMEM, split-K over pixel
 //                     ranges with float atomics into the fp32 gradient.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -356,6 +357,320 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ 3x3, halo reuse
+// tc_conv_halo_kernel: 3x3 / pad 1 / stride 1 convolution for H, W multiples of 16.  tc_conv_kernel above stages one
+// 128-pixel box per filter tap, i.e. every input pixel crosses L2 -> shared memory 9 times, and with <= 256 output
+// channels per tile that traffic (not the tensor pipe) bounds the kernel: the whole chip moves ~6300 B/clk out of L2
+// (~43 B/clk/SM) against 8192 flop/clk/SM, so a tile needs ~190 flop per staged byte; 128 x N tiles give 55 (N=96)
+// to 85 (N=256).  Here a tile is a 16 x 16 pixel square (M = 2 x 128) and one TMA box carries the 18 x 16 pixel
+// block (rows h0-1 .. h0+16, columns shifted by dx-1, 64/32/16 channels) for ONE horizontal tap offset dx.  The
+// three vertical taps of that dx read the same block at smem row offsets dy*16 pixels -- whole multiples of the
+// swizzle atom, so only the descriptor start address moves -- and both 128-pixel halves of the tile share the
+// weight boxes.  Staged bytes per output pixel drop 2.3x (A: 9 x 128 -> 3 x 144 pixel rows per 128 outputs, B halved).
+struct TcHaloParams {
+  int B, H, W, Cout;
+  int tiles_w, tiles_h, n_tiles, total_tiles;
+  int BN, cw, chunks, G, n_units, n_stage_iters, stages;
+  uint32_t a_bytes, b_tx, b_slot, unit_bytes, stage_bytes, swz, idesc;
+  int out_bf16, res_bf16, res_shift, act;
+  void* y;
+  const float* bias;
+  const void* res;
+  const float* alpha;
+};
+
+static constexpr int kHaloT = 16;  // tile edge in pixels
+
+struct HaloTile {
+  int w0, h0, n, co0;
+};
+__device__ __forceinline__ HaloTile decode_halo_tile(const TcHaloParams& p, int tile) {
+  HaloTile t;
+  const int nt = tile % p.n_tiles;
+  int mt = tile / p.n_tiles;
+  const int tw = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  t.w0 = tw * kHaloT;
+  t.h0 = (mt % p.tiles_h) * kHaloT;
+  t.n = mt / p.tiles_h;
+  t.co0 = nt * p.BN;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const TcHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: unit = (channel chunk, dx): one 18x16-pixel A box + three weight boxes
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t unit_tx = p.a_bytes + 3u * p.b_tx;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const HaloTile t = decode_halo_tile(p, tile);
+        int cc = 0, dx = 0, left = p.n_units;
+        for (int it = 0; it < p.n_stage_iters; ++it) {
+          const int n = left < p.G ? left : p.G;
+          left -= n;
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* su = smem + static_cast<size_t>(stage) * p.stage_bytes;
+          mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * unit_tx);
+          for (int g = 0; g < n; ++g) {
+            tma_load_4d(su, &tmA, &full[stage], cc * p.cw, t.w0 + dx - 1, t.h0 - 1, t.n);
+            uint8_t* sb = su + p.a_bytes;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) tma_load_3d(sb + dy * p.b_slot, &tmB, &full[stage], cc * p.cw, dy * 3 + dx, t.co0);
+            su += p.unit_bytes;
+            if (++dx == 3) {
+              dx = 0;
+              ++cc;
+            }
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const int ksteps = p.cw / 16;
+      const uint64_t desc0 = umma_desc_kmajor(0, p.swz);
+      const uint32_t row16 = (static_cast<uint32_t>(kHaloT) * p.swz) >> 4;  // one image row of the block, in 16-byte units
+      const uint32_t b_off = p.a_bytes >> 4, b_step = p.b_slot >> 4, u_step = p.unit_bytes >> 4;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc) * 256u;
+        const uint32_t d1 = d0 + static_cast<uint32_t>(p.BN);
+        int left = p.n_units;
+        uint32_t first = 0;
+        for (int it = 0; it < p.n_stage_iters; ++it) {
+          const int n = left < p.G ? left : p.G;
+          left -= n;
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          uint64_t du = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
+          for (int g = 0; g < n; ++g) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint64_t da0 = du + static_cast<uint32_t>(dy) * row16;        // output rows 0..7  of the tile
+              const uint64_t da1 = da0 + 8u * row16;                              // output rows 8..15
+              const uint64_t db = du + b_off + static_cast<uint32_t>(dy) * b_step;
+              for (int k = 0; k < ksteps; ++k) {
+                umma_bf16(d0, da0 + 2u * k, db + 2u * k, p.idesc, first);
+                umma_bf16(d1, da1 + 2u * k, db + 2u * k, p.idesc, first);
+                first = 1u;
+              }
+            }
+            du += u_step;
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue: each warp owns TMEM lanes [32q, 32q+32) of both 128-pixel halves
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const float alpha = p.alpha ? *p.alpha : 1.f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const HaloTile t = decode_halo_tile(p, tile);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      for (int half = 0; half < 2; ++half) {
+        const int m = half * 128 + row;
+        const int h = t.h0 + (m >> 4), w = t.w0 + (m & 15);
+        const int64_t pix = (static_cast<int64_t>(t.n) * p.H + h) * p.W + w;
+        int64_t rpix = pix;
+        if (p.res_shift) rpix = (static_cast<int64_t>(t.n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u +
+                               static_cast<uint32_t>(half * p.BN);
+        auto emit8 = [&](const uint32_t* rr, int co) {
+          if (co < p.Cout) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = alpha * __uint_as_float(rr[j]);
+            if (p.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.res) {
+              float rv[8];
+              load8(p.res, rpix * p.Cout + co, p.res_bf16, rv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += rv[j];
+            }
+            if (p.act == ICGAN_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (p.act == ICGAN_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+            }
+            store8(p.y, pix * p.Cout + co, p.out_bf16, v);
+          }
+        };
+        int c = 0;
+        for (; c + 32 <= p.BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + static_cast<uint32_t>(c), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) emit8(r + g8 * 8, t.co0 + c + g8 * 8);
+        }
+        for (; c < p.BN; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(c), r);
+          tmem_ld_wait();
+          emit8(r, t.co0 + c);
+          emit8(r + 8, t.co0 + c + 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Returns kHaloIneligible when the shape does not fit (caller falls back to tc_conv_kernel), else 0 / an error code.
+static constexpr int kHaloIneligible = -2;
+static int launch_conv_halo(const void* x, const void* wk, const float* alpha_dev, const float* bias,
+                            const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int out_dtype,
+                            int res_dtype, int res_shift, int act, cudaStream_t stream) {
+  static const int enabled = env_int("ICGAN_TC_HALO", 1);
+  if (!enabled || (H % kHaloT) || (W % kHaloT)) return kHaloIneligible;
+  TcHaloParams p{};
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.tiles_w = W / kHaloT;
+  p.tiles_h = H / kHaloT;
+  static const int cw_override = env_int("ICGAN_TC_HALO_CW", 0);
+  p.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  if (cw_override && cw_override <= p.cw && Cin % cw_override == 0) p.cw = cw_override;
+  // Cin = 96, 160, ...: 64-channel chunks with the last one part out of bounds (TMA zero-fills both operands).
+  static const int pad64 = env_int("ICGAN_TC_HALO_PAD64", 0);
+  if (pad64 && p.cw < 64 && Cin > 64) p.cw = 64;
+  p.swz = static_cast<uint32_t>(p.cw * 2);
+  p.chunks = ceil_div(Cin, p.cw);
+  p.n_units = 3 * p.chunks;
+  if (Cout <= 128) p.BN = (Cout + 15) / 16 * 16;
+  else if (Cout % 128 == 0) p.BN = 128;
+  else if (Cout % 96 == 0) p.BN = 96;
+  else if (Cout % 112 == 0) p.BN = 112;
+  else if (Cout % 80 == 0) p.BN = 80;
+  else if (Cout % 64 == 0) p.BN = 64;
+  else p.BN = 128;
+  p.n_tiles = ceil_div(Cout, p.BN);
+  p.total_tiles = p.tiles_w * p.tiles_h * B * p.n_tiles;
+  p.a_bytes = static_cast<uint32_t>((kHaloT + 2) * kHaloT) * p.swz;
+  p.b_tx = static_cast<uint32_t>(p.BN) * p.swz;
+  p.b_slot = (p.b_tx + 1023u) & ~1023u;
+  p.unit_bytes = p.a_bytes + 3u * p.b_slot;
+  static const int stage_target = env_int("ICGAN_TC_HALO_STAGE_KB", 48) * 1024;
+  int G = stage_target / static_cast<int>(p.unit_bytes);
+  if (G < 1) G = 1;
+  if (G > p.n_units) G = p.n_units;
+  p.G = G;
+  p.n_stage_iters = ceil_div(p.n_units, G);
+  p.stage_bytes = static_cast<uint32_t>(G) * p.unit_bytes;
+  const uint32_t tail = 1024u + 512u;
+  int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return kHaloIneligible;
+  p.stages = stages;
+  p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.BN));
+  p.out_bf16 = out_dtype == ICGAN_BF16;
+  p.res_bf16 = res_dtype == ICGAN_BF16;
+  p.res_shift = res_shift;
+  p.act = act;
+  p.y = y; p.bias = bias; p.res = residual; p.alpha = alpha_dev;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const uint32_t box[4] = {(uint32_t)p.cw, (uint32_t)kHaloT, (uint32_t)(kHaloT + 2), 1u};
+    int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, p.swz);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)Cin, 9ull, (uint64_t)Cout};
+    const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)9 * Cin * 2};
+    const uint32_t box[3] = {(uint32_t)p.cw, 1u, (uint32_t)p.BN};
+    int rc = make_tmap_bf16(&tmB, wk, 3, dims, str, box, p.swz);
+    if (rc) return rc;
+  }
+  const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
+  static bool configured = false;
+  if (!configured) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  tc_conv_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci], operands read straight from the NHWC tensors:
 // the reduction index (pixels) is the ROW of each TMA box and channels are contiguous, i.e. both UMMA operands are
@@ -573,6 +888,12 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   ICGAN_REQUIRE(Cin % 16 == 0 && Cin >= 16, "icgan_conv2d_tc: Cin must be a multiple of 16 (got %d)", Cin);
   ICGAN_REQUIRE(Cout % 8 == 0 && Cout >= 8, "icgan_conv2d_tc: Cout must be a multiple of 8 (got %d)", Cout);
   ICGAN_REQUIRE(!(res_shift && ((H | W) & 1)), "icgan_conv2d_tc: res_shift needs even H, W");
+
+  if (ksize == 3 && !bn_stats) {
+    const int rc = launch_conv_halo(x, wk, alpha_dev, bias, residual, y, B, H, W, Cin, Cout, out_dtype, res_dtype,
+                                    res_shift, act, static_cast<cudaStream_t>(stream));
+    if (rc != kHaloIneligible) return rc;
+  }
 
   TcConvParams p{};
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;

@@ -528,7 +528,8 @@ class ReluSumPoolFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         B, H, W, Cc = x.shape
         dx = torch.empty_like(x)
-        call("icgan_relu_sumpool_bwd", ptr(x), ptr(dh.contiguous().float()), ptr(dx), B, H * W, Cc, dt(x), stream_ptr())
+        dh = dh.contiguous().float()
+        call("icgan_relu_sumpool_bwd", ptr(x), ptr(dh), ptr(dx), B, H * W, Cc, dt(x), stream_ptr())
         return dx
 
 

@@ -42,8 +42,10 @@ def _launch(x, b, xref, yref, dy, grad, dim, spec, alpha, gain, clamp):
         return t.contiguous(memory_format=torch.channels_last) if (x.ndim == 4 and x.stride(1) == 1 and x.shape[1] > 1) \
             else t.contiguous()
     bb = None if b is None else b.to(x.dtype).contiguous()
-    call("icgan_bias_act", ptr(x), ptr(bb), ptr(same(xref)), ptr(same(yref)), ptr(same(dy)), ptr(y), x.numel(),
-         int(step_b), int(size_b), grad, spec.cuda_idx, float(alpha), float(gain), float(clamp), dt(x), stream_ptr())
+    xr, yr, dd = same(xref), same(yref), same(dy)  # keep the (possibly re-laid-out) copies alive across the launch
+    call("icgan_bias_act", ptr(x), ptr(bb), ptr(xr), ptr(yr), ptr(dd), ptr(y), x.numel(), int(step_b), int(size_b), grad,
+         spec.cuda_idx, float(alpha), float(gain), float(clamp), dt(x), stream_ptr())
+    del xr, yr, dd
     return y
 
 

@@ -50,7 +50,8 @@ def _conv_nhwc(x, wk32, bias, stride, pad):
     y = torch.empty(B, ho, wo, co, device=x.device, dtype=x.dtype)
     b32 = None if bias is None else bias.float().contiguous()
     if x.dtype == torch.bfloat16 and stride == 1 and k in (1, 3) and pad == k // 2 and ci % 16 == 0 and co % 8 == 0:
-        call("icgan_conv2d_tc", ptr(x), ptr(wk32.to(torch.bfloat16)), None, ptr(b32), None, ptr(y), None, B, H, W, ci, co,
+        wk16 = wk32.to(torch.bfloat16)
+        call("icgan_conv2d_tc", ptr(x), ptr(wk16), None, ptr(b32), None, ptr(y), None, B, H, W, ci, co,
              k, dt(y), L.F32, 0, L.ACT_NONE, stream_ptr())
     else:
         call("icgan_conv2d_simt", ptr(x), ptr(wk32), None, ptr(b32), None, ptr(y), B, H, W, ci, co, k, stride, pad, dt(x),

@@ -63,7 +63,8 @@ def _run(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)
     oh = (H * upy + pady0 + pady1 - fh + downy) // downy
     y = torch.empty((N, C, oh, ow), device=x.device, dtype=x.dtype,
                     memory_format=torch.channels_last if cl else torch.contiguous_format)
-    call("icgan_upfirdn2d", ptr(x), ptr(f2d.contiguous()), ptr(y), N, C, H, W, fh, fw, upx, upy, downx, downy, padx0,
+    f2d = f2d.contiguous()
+    call("icgan_upfirdn2d", ptr(x), ptr(f2d), ptr(y), N, C, H, W, fh, fw, upx, upy, downx, downy, padx0,
          padx1, pady0, pady1, int(flip), float(gain), int(cl), dt(x), stream_ptr())
     return y
 

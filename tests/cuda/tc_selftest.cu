@@ -238,13 +238,38 @@ static void run_prof() {
   printf("prof launches done\n");
 }
 
+// prof2 <B> <H> <W> <Cin> <Cout>: five launches of one 3x3 conv shape (for ncu -s/-c selection)
+static void run_prof2(int B, int H, int W, int Ci, int Co) {
+  const size_t nx = (size_t)B * H * W * Ci, ny = (size_t)B * H * W * Co, nw = (size_t)Co * 9 * Ci;
+  void *x, *y, *w;
+  CK(cudaMalloc(&x, nx * 2)); CK(cudaMalloc(&y, ny * 2)); CK(cudaMalloc(&w, nw * 2));
+  CK(cudaMemset(x, 0x3c, nx * 2)); CK(cudaMemset(w, 0x3c, nw * 2));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 5; ++i) {
+    CK(cudaEventRecord(e0));
+    int rc = icgan_conv2d_tc(x, w, nullptr, nullptr, nullptr, y, nullptr, B, H, W, Ci, Co, 3, ICGAN_BF16, ICGAN_F32, 0, 0, nullptr);
+    if (rc) { printf("launch error %s\n", icgan_last_error()); exit(2); }
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("prof2 B=%d %dx%d %d->%d : %.3f ms %.1f TFLOP/s\n", B, H, W, Ci, Co, ms, 2.0 * B * H * W * 9.0 * Ci * Co / ms * 1e-9);
+  }
+}
+
 int main(int argc, char** argv) {
+  if (argc > 6 && !strcmp(argv[1], "prof2")) {
+    run_prof2(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]));
+    return 0;
+  }
   // usage: tc_selftest [all|conv|wgrad <idx>|perf|prof]
   const char* mode = argc > 1 ? argv[1] : "all";
   if (!strcmp(mode, "prof")) { run_prof(); return 0; }
-  const bool perf = !strcmp(mode, "perf");
+  const bool convperf = !strcmp(mode, "convperf");  // conv correctness + conv timings only
+  const bool perf = !strcmp(mode, "perf") || convperf;
   const bool do_conv = !strcmp(mode, "all") || !strcmp(mode, "conv") || perf;
-  const bool do_wgrad = !strcmp(mode, "all") || !strcmp(mode, "wgrad") || perf;
+  const bool do_wgrad = !strcmp(mode, "all") || !strcmp(mode, "wgrad") || (perf && !convperf);
   const int only = (argc > 2) ? atoi(argv[2]) : -1;
   int fails = 0;
   const ConvCase conv_cases[] = {
@@ -258,6 +283,12 @@ int main(int argc, char** argv) {
       {"c8_gemm_like", 1, 1, 1536, 2048, 768, 1, 0, 0, 0, 1},
       {"c9_tanh_cout8", 2, 16, 16, 32, 8, 3, 0, 0, ICGAN_ACT_TANH, 1},
       {"c10_many_tiles", 4, 64, 64, 192, 384, 3, 1, 1, 0, 1},
+      // 3x3 shapes with H, W multiples of 16 take the halo-reuse kernel (16x16-pixel tiles, 18-row boxes)
+      {"h1_one_tile", 2, 16, 16, 64, 128, 3, 0, 0, 0, 1},
+      {"h2_cw32_cout24_nonsq", 3, 32, 48, 96, 24, 3, 0, 1, 0, 1},
+      {"h3_cw16_cout200_tail", 2, 64, 64, 48, 200, 3, 1, 0, ICGAN_ACT_RELU, 1},
+      {"h4_res_half_3ntiles", 1, 32, 32, 256, 384, 3, 1, 2, 0, 1},
+      {"h5_many_units", 1, 16, 32, 512, 96, 3, 0, 0, 0, 0},
   };
   if (do_conv)
     for (const ConvCase& c : conv_cases) fails += run_conv_case(c, false);
@@ -287,8 +318,15 @@ int main(int argc, char** argv) {
         {"p3_1536@8", 64, 8, 8, 1536, 1536, 3, 1, 0, 0, 1},
         {"p4_768@32", 32, 32, 32, 768, 768, 3, 1, 0, 0, 1},
         {"p5_192@128", 16, 128, 128, 192, 192, 3, 1, 0, 0, 1},
+        {"p6_192to96@256", 8, 256, 256, 192, 96, 3, 1, 0, 0, 1},
+        {"p7_1536@16", 64, 16, 16, 1536, 1536, 3, 1, 0, 0, 1},
+        {"p8_768to384@64", 32, 64, 64, 768, 384, 3, 1, 0, 0, 1},
     };
     for (const ConvCase& c : perf_cases) fails += run_conv_case(c, true);
+    if (convperf) {
+      printf("TC_SELFTEST %s (%d failing cases)\n", fails ? "FAILED" : "PASSED", fails);
+      return fails ? 1 : 0;
+    }
     const WgradCase wperf[] = {{"wp1_384@64", 32, 64, 64, 384, 384, 3}, {"wp2_96@256", 8, 256, 256, 96, 96, 3},
                                {"wp3_768@32", 32, 32, 32, 768, 768, 3}};
     for (const WgradCase& c : wperf) fails += run_wgrad_case(c, true);
