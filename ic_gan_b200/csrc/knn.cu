@@ -124,7 +124,7 @@ knn_coarse_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   const uint32_t a_bytes = 128u * 128u, b_bytes = kKnnBN * 128u;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp runs the loops (uniform control flow); one elected lane issues the TMA / MMA instructions
       int stage = 0;
       uint32_t phase = 0;
       for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
@@ -135,9 +135,12 @@ knn_coarse_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
             for (int ps = 0; ps < p.passes; ++ps) {  // hi.hi, hi.lo, lo.hi
               mbar_wait(&empty[stage], phase ^ 1u);
               uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
-              mbar_expect_tx(&full[stage], a_bytes + b_bytes);
-              tma_load_2d(sa, ps == 2 ? &tmAlo : &tmAhi, &full[stage], kc * kKnnKC, m0);
-              tma_load_2d(sa + a_bytes, ps == 1 ? &tmBlo : &tmBhi, &full[stage], kc * kKnnKC, n0);
+              if (elect_one_sync()) {
+                mbar_expect_tx(&full[stage], a_bytes + b_bytes);
+                tma_load_2d(sa, ps == 2 ? &tmAlo : &tmAhi, &full[stage], kc * kKnnKC, m0);
+                tma_load_2d(sa + a_bytes, ps == 1 ? &tmBlo : &tmBhi, &full[stage], kc * kKnnKC, n0);
+              }
+              __syncwarp();
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -148,7 +151,7 @@ knn_coarse_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const uint64_t desc0 = umma_desc_kmajor(0, 128);
@@ -164,15 +167,18 @@ knn_coarse_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
             tc_fence_after();
             const uint64_t da = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
             const uint64_t db = da + (a_bytes >> 4);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < kKnnKC / 16; ++k) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (it | k) ? 1u : 0u);
-            umma_commit(&empty[stage]);
+              for (int k = 0; k < kKnnKC / 16; ++k) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (it | k) ? 1u : 0u);
+              umma_commit(&empty[stage]);
+              if (it + 1 == iters) umma_commit(&tfull[acc]);
+            }
+            __syncwarp();
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          umma_commit(&tfull[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1u;
         }

@@ -178,9 +178,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     // One pipeline stage carries up to G k-chunks (G A-boxes + G B-boxes, one barrier round trip), so that the MMA
     // thread always has >= ~4 UMMAs per wait. Tap/chunk counters advance incrementally: no integer division here.
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
+    // The whole warp runs the loops (uniform control flow); one elected lane issues the TMA instructions.
+    {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+      }
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t chunk_tx = p.a_bytes + p.b_tx;
@@ -193,10 +196,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
           uint8_t* sb = sa + static_cast<size_t>(p.G) * p.a_bytes;
-          mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * chunk_tx);
+          const bool leader = elect_one_sync();
+          if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * chunk_tx);
           for (int g = 0; g < n; ++g) {
-            tma_load_4d(sa, &tmA, &full[stage], cc * p.cw, t.w0 + dw, t.h0 + dh, t.n0);
-            tma_load_3d(sb, &tmB, &full[stage], cc * p.cw, tap, t.co0);
+            if (leader) {
+              tma_load_4d(sa, &tmA, &full[stage], cc * p.cw, t.w0 + dw, t.h0 + dh, t.n0);
+              tma_load_3d(sb, &tmB, &full[stage], cc * p.cw, tap, t.co0);
+            }
             sa += p.a_bytes;
             sb += p.b_chunk;
             if (++cc == p.chunks) {
@@ -208,6 +214,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -216,8 +223,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const int ksteps = p.cw / 16;
@@ -235,23 +242,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           left -= n;
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          uint64_t da = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
-          uint64_t db = da + b_off;
-          for (int g = 0; g < n; ++g) {
-            for (int k = 0; k < ksteps; ++k) {  // +32 bytes (16 bf16) along K inside the swizzle atom
-              umma_bf16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, first);
-              first = 1u;
+          const uint64_t da0 = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
+          if (elect_one_sync()) {
+            uint64_t da = da0, db = da0 + b_off;
+            for (int g = 0; g < n; ++g) {
+              for (int k = 0; k < ksteps; ++k) {  // +32 bytes (16 bf16) along K inside the swizzle atom
+                umma_bf16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, first);
+                first = 1u;
+              }
+              da += a_step;
+              db += b_step;
             }
-            da += a_step;
-            db += b_step;
+            umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+            if (it + 1 == p.n_stage_iters) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          first = 1u;
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -433,9 +444,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer: unit = (channel chunk, dx): one 18x16-pixel A box + three weight boxes
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
+    {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+      }
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t unit_tx = p.a_bytes + 3u * p.b_tx;
@@ -447,18 +460,23 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           left -= n;
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* su = smem + static_cast<size_t>(stage) * p.stage_bytes;
-          mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * unit_tx);
+          const bool leader = elect_one_sync();
+          if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * unit_tx);
           for (int g = 0; g < n; ++g) {
-            tma_load_4d(su, &tmA, &full[stage], cc * p.cw, t.w0 + dx - 1, t.h0 - 1, t.n);
-            uint8_t* sb = su + p.a_bytes;
+            if (leader) {
+              tma_load_4d(su, &tmA, &full[stage], cc * p.cw, t.w0 + dx - 1, t.h0 - 1, t.n);
+              uint8_t* sb = su + p.a_bytes;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) tma_load_3d(sb + dy * p.b_slot, &tmB, &full[stage], cc * p.cw, dy * 3 + dx, t.co0);
+              for (int dy = 0; dy < 3; ++dy)
+                tma_load_3d(sb + dy * p.b_slot, &tmB, &full[stage], cc * p.cw, dy * 3 + dx, t.co0);
+            }
             su += p.unit_bytes;
             if (++dx == 3) {
               dx = 0;
               ++cc;
             }
           }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -467,8 +485,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const int ksteps = p.cw / 16;
@@ -487,28 +505,33 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           left -= n;
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          uint64_t du = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
-          for (int g = 0; g < n; ++g) {
+          const uint64_t du0 = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
+          if (elect_one_sync()) {
+            uint64_t du = du0;
+            for (int g = 0; g < n; ++g) {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const uint64_t da0 = du + static_cast<uint32_t>(dy) * row16;        // output rows 0..7  of the tile
-              const uint64_t da1 = da0 + 8u * row16;                              // output rows 8..15
-              const uint64_t db = du + b_off + static_cast<uint32_t>(dy) * b_step;
-              for (int k = 0; k < ksteps; ++k) {
-                umma_bf16(d0, da0 + 2u * k, db + 2u * k, p.idesc, first);
-                umma_bf16(d1, da1 + 2u * k, db + 2u * k, p.idesc, first);
-                first = 1u;
+              for (int dy = 0; dy < 3; ++dy) {
+                const uint64_t da0 = du + static_cast<uint32_t>(dy) * row16;  // output rows 0..7  of the tile
+                const uint64_t da1 = da0 + 8u * row16;                        // output rows 8..15
+                const uint64_t db = du + b_off + static_cast<uint32_t>(dy) * b_step;
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_bf16(d0, da0 + 2u * k, db + 2u * k, p.idesc, first);
+                  umma_bf16(d1, da1 + 2u * k, db + 2u * k, p.idesc, first);
+                  first = 1u;
+                }
               }
+              du += u_step;
             }
-            du += u_step;
+            umma_commit(&empty[stage]);
+            if (it + 1 == p.n_stage_iters) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
           }
-          umma_commit(&empty[stage]);
+          first = 1u;
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -760,9 +783,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   const uint32_t idesc2 = umma_idesc_bf16(128, n2 ? n2 : 64) | (1u << 15) | (1u << 16);
 
   if (warp == 0) {
-    if (lane == 0 && n_chunks > 0) {
-      tma_prefetch_desc(&tmDy);
-      tma_prefetch_desc(&tmX);
+    // whole warp runs the loop (uniform control flow), one elected lane issues the TMA instructions
+    if (n_chunks > 0) {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmDy);
+        tma_prefetch_desc(&tmX);
+      }
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = p.a_bytes + static_cast<uint32_t>(nb) * p.box_bytes;
@@ -779,26 +805,29 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
         }
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
-        mbar_expect_tx(&full[stage], tx);
-        tma_load_4d(sa, &tmDy, &full[stage], co0, w0, h0, n0);
-        tma_load_4d(sa + p.box_bytes, &tmDy, &full[stage], co0 + 64, w0, h0, n0);
-        uint8_t* sb = sa + p.a_bytes;
-        if (p.taps > 1) {
-          int dh = dh0, dw = dw0;
-          for (int j = 0; j < nb; ++j) {
-            tma_load_4d(sb, &tmX, &full[stage], ci0, w0 + dw, h0 + dh, n0);
-            sb += p.box_bytes;
-            if (++dw > p.pad) {
-              dw = -p.pad;
-              ++dh;
+        if (elect_one_sync()) {
+          mbar_expect_tx(&full[stage], tx);
+          tma_load_4d(sa, &tmDy, &full[stage], co0, w0, h0, n0);
+          tma_load_4d(sa + p.box_bytes, &tmDy, &full[stage], co0 + 64, w0, h0, n0);
+          uint8_t* sb = sa + p.a_bytes;
+          if (p.taps > 1) {
+            int dh = dh0, dw = dw0;
+            for (int j = 0; j < nb; ++j) {
+              tma_load_4d(sb, &tmX, &full[stage], ci0, w0 + dw, h0 + dh, n0);
+              sb += p.box_bytes;
+              if (++dw > p.pad) {
+                dw = -p.pad;
+                ++dh;
+              }
+            }
+          } else {
+            for (int j = 0; j < nb; ++j) {
+              tma_load_4d(sb, &tmX, &full[stage], ci0 + 64 * j, w0, h0, n0);
+              sb += p.box_bytes;
             }
           }
-        } else {
-          for (int j = 0; j < nb; ++j) {
-            tma_load_4d(sb, &tmX, &full[stage], ci0 + 64 * j, w0, h0, n0);
-            sb += p.box_bytes;
-          }
         }
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -806,7 +835,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_chunks > 0) {
+    if (n_chunks > 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t desc0 = umma_desc_mnmajor(0, p.box_bytes);
@@ -815,19 +844,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint64_t da = desc0 + (((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < kWgradKP / 16; ++k) {  // 16 pixel rows = 2 swizzle atoms = 2048 bytes per UMMA
-          const uint32_t accf = (it | k) != 0 ? 1u : 0u;
-          umma_bf16(tmem_base, da + 128u * k, da + b_off + 128u * k, idesc1, accf);
-          if (n2) umma_bf16(tmem_base + 256u, da + 128u * k, da + b2_off + 128u * k, idesc2, accf);
+          for (int k = 0; k < kWgradKP / 16; ++k) {  // 16 pixel rows = 2 swizzle atoms = 2048 bytes per UMMA
+            const uint32_t accf = (it | k) != 0 ? 1u : 0u;
+            umma_bf16(tmem_base, da + 128u * k, da + b_off + 128u * k, idesc1, accf);
+            if (n2) umma_bf16(tmem_base + 256u, da + 128u * k, da + b2_off + 128u * k, idesc2, accf);
+          }
+          umma_commit(&empty[stage]);
+          if (it + 1 == n_chunks) umma_commit(&tfull[0]);
         }
-        umma_commit(&empty[stage]);
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(&tfull[0]);
     }
   } else if (n_chunks > 0) {
     const int q = warp & 3;

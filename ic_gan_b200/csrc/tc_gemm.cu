@@ -112,9 +112,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
+    {  // whole warp runs the loops (uniform control flow); one elected lane issues the TMA / MMA instructions
+      if (lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -125,18 +127,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
           uint8_t* sb = sa + p.a_bytes;
-          mbar_expect_tx(&full[stage], p.a_bytes + p.b_tx);
-          if (!p.a_mn) {
-            tma_load_3d(sa, &tmA, &full[stage], k0, m0, b);
-          } else {
-            tma_load_3d(sa, &tmA, &full[stage], m0, k0, b);
-            tma_load_3d(sa + 8192, &tmA, &full[stage], m0 + 64, k0, b);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full[stage], p.a_bytes + p.b_tx);
+            if (!p.a_mn) {
+              tma_load_3d(sa, &tmA, &full[stage], k0, m0, b);
+            } else {
+              tma_load_3d(sa, &tmA, &full[stage], m0, k0, b);
+              tma_load_3d(sa + 8192, &tmA, &full[stage], m0 + 64, k0, b);
+            }
+            if (!p.b_mn) {
+              tma_load_3d(sb, &tmB, &full[stage], k0, n0, b);
+            } else {
+              for (int j = 0; j < p.b_boxes; ++j) tma_load_3d(sb + j * 8192, &tmB, &full[stage], n0 + 64 * j, k0, b);
+            }
           }
-          if (!p.b_mn) {
-            tma_load_3d(sb, &tmB, &full[stage], k0, n0, b);
-          } else {
-            for (int j = 0; j < p.b_boxes; ++j) tma_load_3d(sb + j * 8192, &tmB, &full[stage], n0 + 64 * j, k0, b);
-          }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -145,7 +150,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -160,16 +165,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t da = p.a_mn ? desc_mn(sa, 8192) : umma_desc_kmajor(sa, 128);
           const uint64_t db = p.b_mn ? desc_mn(sb, 8192) : umma_desc_kmajor(sb, 128);
           const uint32_t sa_step = p.a_mn ? 128u : 2u, sb_step = p.b_mn ? 128u : 2u;  // 16 K elements per UMMA
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kKC / 16; ++k)
-            umma_bf16(d_tmem, da + sa_step * k, db + sb_step * k, p.idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+            for (int k = 0; k < kKC / 16; ++k)
+              umma_bf16(d_tmem, da + sa_step * k, db + sb_step * k, p.idesc, (it | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (it + 1 == p.k_iters) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
