@@ -21,7 +21,8 @@
 namespace icgan {
 
 static constexpr int kMaxStages = 12;
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 192;      // 2 role warps + 4 epilogue warps (wgrad, conv with fused BN statistics)
+static constexpr int kConvThreads = 320;  // 2 role warps + 8 epilogue warps
 static constexpr uint32_t kSmemBudget = 227u * 1024u;
 
 // ------------------------------------------------------------------------------------------------ tensor maps
@@ -105,6 +106,93 @@ __device__ __forceinline__ void store8(void* base, int64_t elem_off, int is_bf16
   }
 }
 
+// One 32-lane x NC-column accumulator block: y[pix, co0..co0+NC) = act(alpha * acc + bias + residual).
+// Each epilogue warp has a scheduler to itself, so nothing hides a dependent load: every global load of the block
+// (bias, residual) is issued before the TMEM load is waited for, and only then is anything consumed.
+struct EpiArgs {
+  void* y;
+  const float* bias;
+  const void* res;
+  int Cout, out_bf16, res_bf16, act;
+  float alpha;
+};
+
+template <int NC>
+__device__ __forceinline__ void epilogue_block(const EpiArgs& e, uint32_t taddr, int co0, int64_t pix, int64_t rpix,
+                                               bool valid) {
+  constexpr int NG = NC / 8;
+  uint32_t r[NC];
+  if constexpr (NC == 32) tmem_ld32(taddr, r);
+  else tmem_ld16(taddr, r);
+  float4 bv[2 * NG];
+  uint4 rv[2 * NG];
+  bool on[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) on[g] = valid && (co0 + 8 * g < e.Cout);
+  if (e.bias) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+      if (on[g]) {
+        bv[2 * g] = *reinterpret_cast<const float4*>(e.bias + co0 + 8 * g);
+        bv[2 * g + 1] = *reinterpret_cast<const float4*>(e.bias + co0 + 8 * g + 4);
+      }
+  }
+  if (e.res) {
+    const int64_t ro = rpix * e.Cout + co0;
+    if (e.res_bf16) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+        if (on[g]) rv[2 * g] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(e.res) + ro + 8 * g);
+    } else {
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+        if (on[g]) {
+          rv[2 * g] = *reinterpret_cast<const uint4*>(static_cast<const float*>(e.res) + ro + 8 * g);
+          rv[2 * g + 1] = *reinterpret_cast<const uint4*>(static_cast<const float*>(e.res) + ro + 8 * g + 4);
+        }
+    }
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (!on[g]) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = e.alpha * __uint_as_float(r[8 * g + j]);
+    if (e.bias) {
+      v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
+      v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
+    }
+    if (e.res) {
+      if (e.res_bf16) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[2 * g]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          v[2 * i] += f.x;
+          v[2 * i + 1] += f.y;
+        }
+      } else {
+        const float* f0 = reinterpret_cast<const float*>(&rv[2 * g]);
+        const float* f1 = reinterpret_cast<const float*>(&rv[2 * g + 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] += f0[i];
+          v[4 + i] += f1[i];
+        }
+      }
+    }
+    if (e.act == ICGAN_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (e.act == ICGAN_ACT_TANH) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+    }
+    store8(e.y, pix * e.Cout + co0 + 8 * g, e.out_bf16, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward / dgrad
 struct TcConvParams {
   int B, H, W, Cout;
@@ -140,7 +228,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile
   return t;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// kEpi = 4 (192 threads; the only variant with the BN-statistics epilogue) or 8 epilogue warps (320 threads: two
+// warps per TMEM lane quadrant, alternating 32-column blocks).
+template <int kEpi>
+__global__ void __launch_bounds__(64 + 32 * kEpi, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -161,7 +252,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty[i], kEpi);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -270,9 +361,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int grp = (warp - 2) >> 2;  // kEpi == 8: which of the two warps of this quadrant
     const int row = q * 32 + lane;
     const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
     const float alpha = p.alpha ? *p.alpha : 1.f;
+    const EpiArgs ea{p.y, p.bias, p.res, p.Cout, p.out_bf16, p.res_bf16, p.act, alpha};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -285,6 +378,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u;
+      if (kEpi == 8 || !p.stats) {
+        int c = 0, blk = 0;
+        for (; c + 32 <= p.BN; c += 32, ++blk)
+          if (kEpi == 4 || (blk & 1) == grp) epilogue_block<32>(ea, taddr + static_cast<uint32_t>(c), t.co0 + c, pix, rpix, valid);
+        if (c < p.BN && (kEpi == 4 || (blk & 1) == grp))
+          epilogue_block<16>(ea, taddr + static_cast<uint32_t>(c), t.co0 + c, pix, rpix, valid);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        continue;
+      }
       auto emit8 = [&](const uint32_t* rr, int co) {
         if (valid && co < p.Cout) {
           float v[8];
@@ -408,7 +514,7 @@ __device__ __forceinline__ HaloTile decode_halo_tile(const TcHaloParams& p, int 
   return t;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const TcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -429,7 +535,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_barrier_init();
   }
@@ -537,67 +643,27 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue: each warp owns TMEM lanes [32q, 32q+32) of both 128-pixel halves
+    // ===================== epilogue: 8 warps; warp (q, half) owns TMEM lanes [32q, 32q+32) of one 128-pixel half
     const int q = warp & 3;
-    const int row = q * 32 + lane;
+    const int half = (warp - 2) >> 2;
+    const int m = half * 128 + q * 32 + lane;
     const float alpha = p.alpha ? *p.alpha : 1.f;
+    const EpiArgs ea{p.y, p.bias, p.res, p.Cout, p.out_bf16, p.res_bf16, p.act, alpha};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const HaloTile t = decode_halo_tile(p, tile);
+      const int h = t.h0 + (m >> 4), w = t.w0 + (m & 15);
+      const int64_t pix = (static_cast<int64_t>(t.n) * p.H + h) * p.W + w;
+      int64_t rpix = pix;
+      if (p.res_shift) rpix = (static_cast<int64_t>(t.n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      for (int half = 0; half < 2; ++half) {
-        const int m = half * 128 + row;
-        const int h = t.h0 + (m >> 4), w = t.w0 + (m & 15);
-        const int64_t pix = (static_cast<int64_t>(t.n) * p.H + h) * p.W + w;
-        int64_t rpix = pix;
-        if (p.res_shift) rpix = (static_cast<int64_t>(t.n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u +
-                               static_cast<uint32_t>(half * p.BN);
-        auto emit8 = [&](const uint32_t* rr, int co) {
-          if (co < p.Cout) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = alpha * __uint_as_float(rr[j]);
-            if (p.bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.res) {
-              float rv[8];
-              load8(p.res, rpix * p.Cout + co, p.res_bf16, rv);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += rv[j];
-            }
-            if (p.act == ICGAN_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (p.act == ICGAN_ACT_TANH) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
-            }
-            store8(p.y, pix * p.Cout + co, p.out_bf16, v);
-          }
-        };
-        int c = 0;
-        for (; c + 32 <= p.BN; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + static_cast<uint32_t>(c), r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) emit8(r + g8 * 8, t.co0 + c + g8 * 8);
-        }
-        for (; c < p.BN; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + static_cast<uint32_t>(c), r);
-          tmem_ld_wait();
-          emit8(r, t.co0 + c);
-          emit8(r + 8, t.co0 + c + 8);
-        }
-      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u +
+                             static_cast<uint32_t>(half * p.BN);
+      int c = 0;
+      for (; c + 32 <= p.BN; c += 32) epilogue_block<32>(ea, taddr + static_cast<uint32_t>(c), t.co0 + c, pix, rpix, true);
+      if (c < p.BN) epilogue_block<16>(ea, taddr + static_cast<uint32_t>(c), t.co0 + c, pix, rpix, true);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -689,7 +755,7 @@ static int launch_conv_halo(const void* x, const void* wk, const float* alpha_de
     configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  tc_conv_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  tc_conv_halo_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmA, tmB, p);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -990,13 +1056,15 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
     if (rc) return rc;
   }
   const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
-  static uint32_t configured = 0;
-  if (smem_bytes > configured) {
-    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = kSmemBudget;
+  static bool configured = false;
+  if (!configured) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  tc_conv_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  if (bn_stats) tc_conv_kernel<4><<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  else tc_conv_kernel<8><<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }
