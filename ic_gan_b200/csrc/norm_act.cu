@@ -428,9 +428,11 @@ extern "C" int icgan_bn_apply(const void* x, void* y, const float* mean, const f
   ICGAN_REQUIRE(x && y && mean && invstd && gain && bias, "icgan_bn_apply: null pointer");
   const int64_t total = static_cast<int64_t>(B) * H * W * C;
   if (in_dtype == ICGAN_BF16 && out_dtype == ICGAN_BF16 && vec::ok(C)) {
-    vec::bn_apply_vec_kernel<<<vec::blocks_for(total / 8), vec::kThreads, 0, STREAM>>>(
-        static_cast<const vec::bf16*>(x), static_cast<vec::bf16*>(y), mean, invstd, gain, bias, gain_stride, B, H, W, C,
-        relu, up);
+    int slabs;
+    const int ppb = vec::slab_grid(B, H * W, &slabs);
+    vec::bn_apply_vec_kernel<<<dim3(static_cast<unsigned>(slabs), static_cast<unsigned>(B)), vec::kThreads, 0, STREAM>>>(
+        static_cast<const vec::bf16*>(x), static_cast<vec::bf16*>(y), mean, invstd, gain, bias, gain_stride, H, W, C,
+        relu, up, ppb);
     ICGAN_LAUNCH_CHECK();
     return 0;
   }
@@ -456,9 +458,15 @@ extern "C" int icgan_bn_bwd_reduce(const void* x, const void* dy, const float* m
     if (vs < 1) vs = 1;
     const int vppb = (HW + vs - 1) / vs;
     vs = (HW + vppb - 1) / vppb;
-    vec::bn_bwd_reduce_vec_kernel<<<dim3(static_cast<unsigned>(vs), static_cast<unsigned>(B)), vec::kThreads, 0,
-                                    STREAM>>>(static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), mean,
-                                              invstd, gain, bias, gain_stride, s1, s2, H, W, C, relu, up, vppb);
+    const dim3 vgrid(static_cast<unsigned>(vs), static_cast<unsigned>(B));
+    if (up)
+      vec::bn_bwd_reduce_vec_kernel<false><<<vgrid, vec::kThreads, 0, STREAM>>>(
+          static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), mean, invstd, gain, bias, gain_stride, s1,
+          s2, H, W, C, relu, up, vppb);
+    else
+      vec::bn_bwd_reduce_vec_kernel<true><<<vgrid, vec::kThreads, 0, STREAM>>>(
+          static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), mean, invstd, gain, bias, gain_stride, s1,
+          s2, H, W, C, relu, up, vppb);
     ICGAN_LAUNCH_CHECK();
     return 0;
   }
@@ -485,9 +493,17 @@ extern "C" int icgan_bn_bwd_apply(const void* x, const void* dy, void* dx, const
   ICGAN_REQUIRE(x && dy && dx && m1 && m2, "icgan_bn_bwd_apply: null pointer");
   const int64_t total = static_cast<int64_t>(B) * H * W * C;
   if (x_dtype == ICGAN_BF16 && dy_dtype == ICGAN_BF16 && vec::ok(C)) {
-    vec::bn_bwd_apply_vec_kernel<<<vec::blocks_for(total / 8), vec::kThreads, 0, STREAM>>>(
-        static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), static_cast<vec::bf16*>(dx), mean, invstd,
-        gain, bias, gain_stride, m1, m2, B, H, W, C, relu, up);
+    int slabs;
+    const int ppb = vec::slab_grid(B, H * W, &slabs);
+    const dim3 vgrid(static_cast<unsigned>(slabs), static_cast<unsigned>(B));
+    if (up)
+      vec::bn_bwd_apply_vec_kernel<false><<<vgrid, vec::kThreads, 0, STREAM>>>(
+          static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), static_cast<vec::bf16*>(dx), mean, invstd,
+          gain, bias, gain_stride, m1, m2, H, W, C, relu, up, ppb);
+    else
+      vec::bn_bwd_apply_vec_kernel<true><<<vgrid, vec::kThreads, 0, STREAM>>>(
+          static_cast<const vec::bf16*>(x), static_cast<const vec::bf16*>(dy), static_cast<vec::bf16*>(dx), mean, invstd,
+          gain, bias, gain_stride, m1, m2, H, W, C, relu, up, ppb);
     ICGAN_LAUNCH_CHECK();
     return 0;
   }

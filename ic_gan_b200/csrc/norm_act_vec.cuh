@@ -21,6 +21,16 @@ __device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
     v[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void cvt8(const uint4& raw, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+constexpr int kUnroll = 4;  // pixels per thread and loop trip in the streaming kernels (memory-level parallelism)
 __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
   uint4 raw;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
@@ -35,26 +45,26 @@ __device__ __forceinline__ void ldf8(const float* p, float (&v)[8]) {
 
 constexpr int kThreads = 256;
 
-// block-level: sum acc[NA] over the pixel lanes (py) of the block, then atomicAdd to dst[j][c0 + i]
+// block-level: sum acc[NA] over the pixel lanes (py) of the block, then atomicAdd to dst[j][c]: the partials go to
+// shared memory as [py][C]; thread c adds up column c (conflict-free, one channel per thread) and issues one atomic.
 template <int NA>
-__device__ __forceinline__ void block_reduce_atomic(float (&acc)[NA][8], float* const (&dst)[NA], int c0, int cg, int py,
+__device__ __forceinline__ void block_reduce_atomic(float (&acc)[NA][8], float* const (&dst)[NA], int /*c0*/, int cg, int py,
                                                     int CG, int PY, bool active) {
   __shared__ float sm[kThreads * 8];
+  const int C = CG * 8;
 #pragma unroll
   for (int j = 0; j < NA; ++j) {
     __syncthreads();
     if (active) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sm[(py * CG + cg) * 8 + i] = acc[j][i];
+      for (int i = 0; i < 8; ++i) sm[py * C + cg * 8 + i] = acc[j][i];
     }
     __syncthreads();
-    if (active && py == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float s = 0.f;
-        for (int y = 0; y < PY; ++y) s += sm[(y * CG + cg) * 8 + i];
-        atomicAdd(dst[j] + c0 + i, s);
-      }
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      float s = 0.f;
+#pragma unroll 4
+      for (int y = 0; y < PY; ++y) s += sm[y * C + c];
+      atomicAdd(dst[j] + c, s);
     }
   }
 }
@@ -74,14 +84,23 @@ shifted_moments_vec_kernel(const bf16* __restrict__ x, const float* __restrict__
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = sh[i] = 0.f;
   if (shift) ldf8(shift + cg * 8, sh);
   if (active) {
-    for (int64_t p = p0 + py; p < p1; p += PY) {
-      float v[8];
-      ld8(x + p * C + cg * 8, v);
+    const bf16* xc = x + cg * 8;
+    for (int64_t p = p0 + py; p < p1; p += kUnroll * PY) {  // kUnroll independent 16-byte loads in flight per thread
+      uint4 raw[kUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = v[i] - sh[i];
-        acc[0][i] += d;
-        acc[1][i] = fmaf(d, d, acc[1][i]);
+      for (int u = 0; u < kUnroll; ++u)
+        if (p + u * PY < p1) raw[u] = *reinterpret_cast<const uint4*>(xc + (p + u * PY) * C);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (p + u * PY >= p1) break;
+        float v[8];
+        cvt8(raw[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[i] - sh[i];
+          acc[0][i] += d;
+          acc[1][i] = fmaf(d, d, acc[1][i]);
+        }
       }
     }
   }
@@ -110,16 +129,25 @@ colsum_vec_kernel(const bf16* __restrict__ x, float* __restrict__ ws, int64_t P,
     for (int i = 0; i < 8; ++i) mean[i] *= invP;
   }
   if (active) {
-    for (int64_t p = p0 + py; p < p1; p += PY) {
-      float v[8];
-      ld8(x + p * C + cg * 8, v);
+    const bf16* xc = x + cg * 8;
+    for (int64_t p = p0 + py; p < p1; p += kUnroll * PY) {
+      uint4 raw[kUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (PASS == 2) {
-          const float d = v[i] - mean[i];
-          acc[0][i] = fmaf(d, d, acc[0][i]);
-        } else {
-          acc[0][i] += v[i];
+      for (int u = 0; u < kUnroll; ++u)
+        if (p + u * PY < p1) raw[u] = *reinterpret_cast<const uint4*>(xc + (p + u * PY) * C);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (p + u * PY >= p1) break;
+        float v[8];
+        cvt8(raw[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (PASS == 2) {
+            const float d = v[i] - mean[i];
+            acc[0][i] = fmaf(d, d, acc[0][i]);
+          } else {
+            acc[0][i] += v[i];
+          }
         }
       }
     }
@@ -128,40 +156,53 @@ colsum_vec_kernel(const bf16* __restrict__ x, float* __restrict__ ws, int64_t P,
   block_reduce_atomic<1>(acc, dst, cg * 8, cg, py, CG, PY, active);
 }
 
-// ---- y = [up2]([relu](xhat * gain[n,c] + bias[n,c]))
+// ---- y = [up2]([relu](xhat * gain[n,c] + bias[n,c]))      grid: (pixel slabs, n)
+// A thread keeps one 8-channel group (its mean / invstd / gain / bias live in registers: re-reading them per element
+// made the kernel L1-bandwidth bound at ~3.6 TB/s) and walks the pixels of its slab, kUnroll loads in flight.
 __global__ void __launch_bounds__(kThreads)
 bn_apply_vec_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gain, const float* __restrict__ bias,
-                    int gstride, int B, int H, int W, int C, int relu, int up) {
-  const int CG = C >> 3;
-  const int64_t total = static_cast<int64_t>(B) * H * W * CG;
-  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(t % CG) * 8;
-    const int64_t pix = t / CG;
-    const int n = static_cast<int>(pix / (static_cast<int64_t>(H) * W));
-    float v[8], m[8], is[8], g[8], b[8];
-    ld8(x + pix * C + c0, v);
-    ldf8(mean + c0, m);
-    ldf8(invstd + c0, is);
-    ldf8(gain + static_cast<int64_t>(n) * gstride + c0, g);
-    ldf8(bias + static_cast<int64_t>(n) * gstride + c0, b);
+                    int gstride, int H, int W, int C, int relu, int up, int pix_per_block) {
+  const int CG = C >> 3, PY = kThreads / CG;
+  const int cg = threadIdx.x % CG, py = threadIdx.x / CG;
+  if (py >= PY) return;
+  const int n = blockIdx.y, c0 = cg * 8;
+  const int HW = H * W;
+  const int q0 = blockIdx.x * pix_per_block, q1 = min(HW, q0 + pix_per_block);
+  float m[8], is[8], g[8], b[8];
+  ldf8(mean + c0, m);
+  ldf8(invstd + c0, is);
+  ldf8(gain + static_cast<int64_t>(n) * gstride + c0, g);
+  ldf8(bias + static_cast<int64_t>(n) * gstride + c0, b);
+  const bf16* xn = x + static_cast<int64_t>(n) * HW * C + c0;
+  bf16* yn = y + static_cast<int64_t>(n) * HW * C * (up ? 4 : 1) + c0;
+  for (int q = q0 + py; q < q1; q += kUnroll * PY) {
+    uint4 raw[kUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float o = (v[i] - m[i]) * is[i] * g[i] + b[i];
-      v[i] = relu ? fmaxf(o, 0.f) : o;
-    }
-    if (!up) {
-      st8(y + pix * C + c0, v);
-    } else {
-      const int w = static_cast<int>(pix % W);
-      const int h = static_cast<int>((pix / W) % H);
-      bf16* o = y + ((static_cast<int64_t>(n) * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c0;
-      const int64_t rs = static_cast<int64_t>(2) * W * C;
-      st8(o, v);
-      st8(o + C, v);
-      st8(o + rs, v);
-      st8(o + rs + C, v);
+    for (int u = 0; u < kUnroll; ++u)
+      if (q + u * PY < q1) raw[u] = *reinterpret_cast<const uint4*>(xn + static_cast<int64_t>(q + u * PY) * C);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int qq = q + u * PY;
+      if (qq >= q1) break;
+      float v[8];
+      cvt8(raw[u], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float o = (v[i] - m[i]) * is[i] * g[i] + b[i];
+        v[i] = relu ? fmaxf(o, 0.f) : o;
+      }
+      if (!up) {
+        st8(yn + static_cast<int64_t>(qq) * C, v);
+      } else {
+        const int h = qq / W, w = qq - h * W;
+        bf16* o = yn + (static_cast<int64_t>(2 * h) * 2 * W + 2 * w) * C;
+        const int64_t rs = static_cast<int64_t>(2) * W * C;
+        st8(o, v);
+        st8(o + C, v);
+        st8(o + rs, v);
+        st8(o + rs + C, v);
+      }
     }
   }
 }
@@ -192,6 +233,8 @@ __device__ __forceinline__ void bn_grad8(const bf16* x, const bf16* dy, const fl
 }
 
 // s1[n,c] += sum_hw g ; s2[n,c] += sum_hw g*xhat    grid: (pixel slabs, n)
+// kTwo: two pixels per trip (plain layers: 2 x 2 loads in flight); upsampled layers already have 5 loads per pixel.
+template <bool kTwo>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ gain,
@@ -212,13 +255,20 @@ bn_bwd_reduce_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy
     ldf8(invstd + c0, is);
     ldf8(gain + static_cast<int64_t>(n) * gstride + c0, g);
     ldf8(bias + static_cast<int64_t>(n) * gstride + c0, b);
-    for (int q = q0 + py; q < q1; q += PY) {
-      float xh[8], gr[8];
-      bn_grad8(x, dy, m, is, g, b, n, q / W, q % W, c0, H, W, C, relu, up, xh, gr);
+    constexpr int NP = kTwo ? 2 : 1;
+    for (int q = q0 + py; q < q1; q += NP * PY) {
+      float xh[NP][8], gr[NP][8];
+      const int qb = q + PY;
+      bn_grad8(x, dy, m, is, g, b, n, q / W, q % W, c0, H, W, C, relu, up, xh[0], gr[0]);
+      if (kTwo && qb < q1) bn_grad8(x, dy, m, is, g, b, n, qb / W, qb % W, c0, H, W, C, relu, up, xh[NP - 1], gr[NP - 1]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[0][i] += gr[i];
-        acc[1][i] = fmaf(gr[i], xh[i], acc[1][i]);
+      for (int u = 0; u < NP; ++u) {
+        if (u == 1 && qb >= q1) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += gr[u][i];
+          acc[1][i] = fmaf(gr[u][i], xh[u][i], acc[1][i]);
+        }
       }
     }
   }
@@ -226,34 +276,42 @@ bn_bwd_reduce_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy
   block_reduce_atomic<2>(acc, dst, c0, cg, py, CG, PY, active);
 }
 
-// dx = invstd * (gain * g - m1 - xhat * m2)
+// dx = invstd * (gain * g - m1 - xhat * m2)      grid: (pixel slabs, n); per-channel parameters in registers
+template <bool kTwo>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gain, const float* __restrict__ bias, int gstride,
-                        const float* __restrict__ m1, const float* __restrict__ m2, int B, int H, int W, int C, int relu,
-                        int up) {
-  const int CG = C >> 3;
-  const int64_t total = static_cast<int64_t>(B) * H * W * CG;
-  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(t % CG) * 8;
-    const int64_t pix = t / CG;
-    const int w = static_cast<int>(pix % W);
-    const int h = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<int64_t>(H) * W));
-    float m[8], is[8], g[8], b[8], a1[8], a2[8], xh[8], gr[8];
-    ldf8(mean + c0, m);
-    ldf8(invstd + c0, is);
-    ldf8(gain + static_cast<int64_t>(n) * gstride + c0, g);
-    ldf8(bias + static_cast<int64_t>(n) * gstride + c0, b);
-    ldf8(m1 + c0, a1);
-    ldf8(m2 + c0, a2);
-    bn_grad8(x, dy, m, is, g, b, n, h, w, c0, H, W, C, relu, up, xh, gr);
-    float o[8];
+                        const float* __restrict__ m1, const float* __restrict__ m2, int H, int W, int C, int relu,
+                        int up, int pix_per_block) {
+  const int CG = C >> 3, PY = kThreads / CG;
+  const int cg = threadIdx.x % CG, py = threadIdx.x / CG;
+  if (py >= PY) return;
+  const int n = blockIdx.y, c0 = cg * 8;
+  const int HW = H * W;
+  const int q0 = blockIdx.x * pix_per_block, q1 = min(HW, q0 + pix_per_block);
+  float m[8], is[8], g[8], b[8], a1[8], a2[8];
+  ldf8(mean + c0, m);
+  ldf8(invstd + c0, is);
+  ldf8(gain + static_cast<int64_t>(n) * gstride + c0, g);
+  ldf8(bias + static_cast<int64_t>(n) * gstride + c0, b);
+  ldf8(m1 + c0, a1);
+  ldf8(m2 + c0, a2);
+  bf16* dxn = dx + static_cast<int64_t>(n) * HW * C + c0;
+  constexpr int NP = kTwo ? 2 : 1;
+  for (int q = q0 + py; q < q1; q += NP * PY) {
+    float xh[NP][8], gr[NP][8];
+    const int qb = q + PY;
+    bn_grad8(x, dy, m, is, g, b, n, q / W, q % W, c0, H, W, C, relu, up, xh[0], gr[0]);
+    if (kTwo && qb < q1) bn_grad8(x, dy, m, is, g, b, n, qb / W, qb % W, c0, H, W, C, relu, up, xh[NP - 1], gr[NP - 1]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = is[i] * (g[i] * gr[i] - a1[i] - xh[i] * a2[i]);
-    st8(dx + pix * C + c0, o);
+    for (int u = 0; u < NP; ++u) {
+      if (u == 1 && qb >= q1) break;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = is[i] * (g[i] * gr[u][i] - a1[i] - xh[u][i] * a2[i]);
+      st8(dxn + static_cast<int64_t>(u ? qb : q) * C, o);
+    }
   }
 }
 
@@ -385,6 +443,15 @@ inline int blocks_for(int64_t work_items) {
   return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
 }
 inline bool ok(int C) { return C % 8 == 0 && C / 8 <= kThreads; }
+// (pixel slabs, samples) grid of ~16 blocks per SM; returns pixels per block
+inline int slab_grid(int B, int HW, int* slabs_out) {
+  int slabs = (16 * num_sms() + B - 1) / B;
+  if (slabs > (HW + 31) / 32) slabs = (HW + 31) / 32;
+  if (slabs < 1) slabs = 1;
+  const int ppb = (HW + slabs - 1) / slabs;
+  *slabs_out = (HW + ppb - 1) / ppb;
+  return ppb;
+}
 
 }  // namespace vec
 }  // namespace

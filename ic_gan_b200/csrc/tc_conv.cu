@@ -760,6 +760,23 @@ static int launch_conv_halo(const void* x, const void* wk, const float* alpha_de
   return 0;
 }
 
+// Split-K factor of the weight-gradient kernels: `items` output tiles x `splits` pixel ranges = CTAs (one per SM at a
+// time, `rounds` waves of them), each walking ceil(k_chunks / splits) stages plus a fixed prologue/epilogue worth about
+// 16 stages.  The old rule (2 * SMs / items) often produced e.g. 2.2 waves, i.e. a third wave at 20 % occupancy.
+static int choose_splits(int items, int k_chunks) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 160 && s <= k_chunks; ++s) {
+    const int rounds = ceil_div(items * s, num_sms());
+    const double cost = static_cast<double>(rounds) * (ceil_div(k_chunks, s) + 16.0);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci], operands read straight from the NHWC tensors:
 // the reduction index (pixels) is the ROW of each TMA box and channels are contiguous, i.e. both UMMA operands are
@@ -954,6 +971,214 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, halo reuse
+// tc_wgrad_halo_kernel: 3x3 weight gradient for W % 16 == 0, H % 4 == 0.  Same MN-major formulation as tc_wgrad_kernel,
+// but a CTA owns ONE horizontal tap offset dx and up to 256 output channels:
+//   * a stage holds 64 pixels (16 wide x 4 rows): up to four 64-channel dY boxes (A, M = 2 x 128) and one X box of
+//     (4+2) x 16 pixels loaded at column offset dx-1 (B);
+//   * the three vertical taps are the same X box viewed at row offsets dy*16 pixels (2048 bytes), i.e. three
+//     "column groups" of one MN-major operand whose leading-dimension stride is 2048 bytes (the groups overlap in
+//     shared memory, which only matters to the address generator): ONE UMMA with N = 192 covers them.
+// Staged rows per flop drop 1.5x against tc_wgrad_kernel (which reloads X for every tap and dY for both tap groups).
+struct TcWgradHaloParams {
+  int Cin, Cout;
+  int tiles_w, tiles_h, k_chunks;
+  int co_tiles, ci_tiles, splits, stages;
+  uint32_t stage_bytes;
+  float* dwk;
+};
+static constexpr uint32_t kWhBox = 64u * 128u;       // one dY box: 64 pixels x 64 channels
+static constexpr uint32_t kWhXBox = 96u * 128u;      // X box: (4+2) x 16 pixels x 64 channels
+static constexpr uint32_t kWhRow = 16u * 128u;       // one image row of a box (16 pixels)
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                     const TcWgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item: (co tile, ci tile, dx, pixel-chunk range)
+  int wi = blockIdx.x;
+  const int split = wi % p.splits;
+  wi /= p.splits;
+  const int dx = wi % 3;
+  wi /= 3;
+  const int ci_t = wi % p.ci_tiles;
+  const int co_t = wi / p.ci_tiles;
+  const int per = (p.k_chunks + p.splits - 1) / p.splits;
+  const int kc_begin = split * per;
+  const int kc_end = min(p.k_chunks, kc_begin + per);
+  const int n_chunks = max(0, kc_end - kc_begin);
+  const int co0 = co_t * 256, ci0 = ci_t * 64;
+  const int mb = min(4, (p.Cout - co0 + 63) / 64);  // 64-channel dY boxes of this tile
+  const int halves = mb > 2 ? 2 : 1;
+  const uint32_t idesc = umma_idesc_bf16(128, 192) | (1u << 15) | (1u << 16);  // A and B MN-major
+
+  if (warp == 0) {
+    if (n_chunks > 0) {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmDy);
+        tma_prefetch_desc(&tmX);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = static_cast<uint32_t>(mb) * kWhBox + kWhXBox;
+      const int per_img = p.tiles_w * p.tiles_h;
+      int tw = kc_begin % p.tiles_w, th = (kc_begin / p.tiles_w) % p.tiles_h, tb = kc_begin / per_img;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        const int w0 = tw * 16, h0 = th * 4, n0 = tb;
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            ++tb;
+          }
+        }
+        mbar_wait(&empty[stage], phase ^ 1u);
+        uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
+        if (elect_one_sync()) {
+          mbar_expect_tx(&full[stage], tx);
+          for (int j = 0; j < mb; ++j) tma_load_4d(sa + j * kWhBox, &tmDy, &full[stage], co0 + 64 * j, w0, h0, n0);
+          tma_load_4d(sa + 4u * kWhBox, &tmX, &full[stage], ci0, w0 + dx - 1, h0 - 1, n0);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (n_chunks > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint64_t desc_a0 = umma_desc_mnmajor(0, kWhBox);  // two 64-channel dY boxes = M 128
+      const uint64_t desc_b0 = umma_desc_mnmajor(0, kWhRow);  // three dy views of the X box, 16 pixel rows apart = N 192
+      for (int it = 0; it < n_chunks; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sbase = ((base + static_cast<uint32_t>(stage) * p.stage_bytes) & 0x3FFFFu) >> 4;
+        const uint64_t da = desc_a0 + sbase;
+        const uint64_t db = desc_b0 + sbase + ((4u * kWhBox) >> 4);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 pixels (one image row of the tile) per UMMA
+            const uint32_t accf = (it | k) != 0 ? 1u : 0u;
+            umma_bf16(tmem_base, da + 128u * k, db + 128u * k, idesc, accf);
+            if (halves == 2) umma_bf16(tmem_base + 256u, da + ((2u * kWhBox) >> 4) + 128u * k, db + 128u * k, idesc, accf);
+          }
+          umma_commit(&empty[stage]);
+          if (it + 1 == n_chunks) umma_commit(&tfull[0]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (n_chunks > 0) {
+    const int q = warp & 3;
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    for (int hf = 0; hf < halves; ++hf) {
+      const int co = co0 + hf * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(hf) * 256u;
+      for (int dy = 0; dy < 3; ++dy) {
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(dy * 64 + c), r);
+          tmem_ld_wait();
+          if (co < p.Cout) {
+            float* dst = p.dwk + (static_cast<int64_t>(co) * 9 + dy * 3 + dx) * p.Cin + ci0 + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (ci0 + c + i < p.Cin) atomicAdd(dst + i, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static constexpr int kWgradHaloIneligible = -2;
+static int launch_wgrad_halo(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin, int Cout,
+                             cudaStream_t stream) {
+  // Measured (r01, bench step): 1.12-1.29x over tc_wgrad_kernel for Cin, Cout >= 192, 0.6-0.9x for 96-channel layers
+  // (one M half, so only N = 192 per staged dY box instead of 320) -> mode 1 (default) takes the wide layers only.
+  static const int mode = env_int("ICGAN_TC_WGRAD_HALO", 1);  // 0 off, 1 wide layers, 2 every eligible shape
+  if (!mode || (W % 16) || (H % 4)) return kWgradHaloIneligible;
+  if (mode == 1 && (Cin < 192 || Cout < 192)) return kWgradHaloIneligible;
+  TcWgradHaloParams p{};
+  p.Cin = Cin; p.Cout = Cout;
+  p.tiles_w = W / 16;
+  p.tiles_h = H / 4;
+  p.k_chunks = p.tiles_w * p.tiles_h * B;
+  p.co_tiles = ceil_div(Cout, 256);
+  p.ci_tiles = ceil_div(Cin, 64);
+  p.stage_bytes = 4u * kWhBox + kWhXBox;  // 44 KB (the dY slots of a narrow tile stay unused)
+  const uint32_t tail = 1024u + 512u;
+  int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const int out_tiles = p.co_tiles * p.ci_tiles * 3;
+  p.splits = choose_splits(out_tiles, p.k_chunks);
+  p.dwk = dwk;
+
+  CUtensorMap tmDy, tmX;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    const uint32_t box[4] = {64u, 16u, 4u, 1u};
+    int rc = make_tmap_bf16(&tmDy, dy, 4, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const uint32_t box[4] = {64u, 16u, 6u, 1u};
+    int rc = make_tmap_bf16(&tmX, x, 4, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
+  static bool configured = false;
+  if (!configured) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = true;
+  }
+  const int grid = out_tiles * p.splits;
+  tc_wgrad_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmDy, tmX, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
 // NHWC [P][C] (f32 or bf16) -> [C][P] bf16 through a padded shared-memory tile.
 template <typename T>
 __global__ void nhwc_to_cnhw_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ xT, int64_t P, int C) {
@@ -1076,6 +1301,11 @@ extern "C" int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, 
   ICGAN_REQUIRE(Cin % 16 == 0 && Cout % 8 == 0, "icgan_conv2d_wgrad_tc: need Cin%%16==0, Cout%%8==0 (got %d, %d)", Cin,
                 Cout);
 
+  if (ksize == 3) {
+    const int rc = launch_wgrad_halo(x, dy, dwk, B, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
+    if (rc != kWgradHaloIneligible) return rc;
+  }
+
   TcWgradParams p{};
   p.Cin = Cin; p.Cout = Cout; p.ksz = ksize; p.pad = ksize / 2; p.taps = ksize * ksize;
   p.TW = pow2_floor(W < kWgradKP ? W : kWgradKP);
@@ -1103,10 +1333,14 @@ extern "C" int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, 
   ICGAN_REQUIRE(stages >= 2, "icgan_conv2d_wgrad_tc: tile does not fit shared memory");
   p.stages = stages;
   const int out_tiles = p.co_tiles * p.ci_tiles * p.groups;
-  int splits = ceil_div(2 * num_sms(), out_tiles);
-  if (splits > p.k_chunks) splits = p.k_chunks;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
+  static const int old_splits = env_int("ICGAN_TC_WGRAD_OLD_SPLITS", 0);
+  if (old_splits) {
+    int splits = ceil_div(2 * num_sms(), out_tiles);
+    if (splits > p.k_chunks) splits = p.k_chunks;
+    p.splits = splits < 1 ? 1 : splits;
+  } else {
+    p.splits = choose_splits(out_tiles, p.k_chunks);
+  }
   p.dwk = dwk;
 
   CUtensorMap tmDy, tmX;

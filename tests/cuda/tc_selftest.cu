@@ -303,6 +303,8 @@ int main(int argc, char** argv) {
       {"w7_3x3_4x4", 24, 4, 4, 128, 256, 3},
       {"w8_1x1_cin96", 2, 32, 32, 96, 192, 1},
       {"w9_3x3_cout24", 2, 16, 16, 48, 24, 3},
+      {"w10_halo_mb3_nonsq", 2, 32, 16, 80, 192, 3},
+      {"w11_halo_h4", 3, 4, 16, 64, 320, 3},
   };
   if (do_wgrad) {
     int i = 0;
