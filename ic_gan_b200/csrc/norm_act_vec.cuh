@@ -233,8 +233,8 @@ __device__ __forceinline__ void bn_grad8(const bf16* x, const bf16* dy, const fl
 }
 
 // s1[n,c] += sum_hw g ; s2[n,c] += sum_hw g*xhat    grid: (pixel slabs, n)
-// kTwo: two pixels per trip (plain layers: 2 x 2 loads in flight); upsampled layers already have 5 loads per pixel.
-template <bool kTwo>
+// kPlain: dy has the resolution of x (host passes up == 0); upsampled layers sum 2x2 children of dy per pixel.
+template <bool kPlain>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ gain,
@@ -255,19 +255,42 @@ bn_bwd_reduce_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy
     ldf8(invstd + c0, is);
     ldf8(gain + static_cast<int64_t>(n) * gstride + c0, g);
     ldf8(bias + static_cast<int64_t>(n) * gstride + c0, b);
-    constexpr int NP = kTwo ? 2 : 1;
-    for (int q = q0 + py; q < q1; q += NP * PY) {
-      float xh[NP][8], gr[NP][8];
-      const int qb = q + PY;
-      bn_grad8(x, dy, m, is, g, b, n, q / W, q % W, c0, H, W, C, relu, up, xh[0], gr[0]);
-      if (kTwo && qb < q1) bn_grad8(x, dy, m, is, g, b, n, qb / W, qb % W, c0, H, W, C, relu, up, xh[NP - 1], gr[NP - 1]);
+    if constexpr (kPlain) {
+      // plain (not upsampled) layer: kUnroll pixels per trip; every load is issued (index clamped, so unconditional)
+      // before anything is consumed -- 2 * kUnroll 16-byte loads in flight per thread.
+      const bf16* xn = x + static_cast<int64_t>(n) * HW * C + c0;
+      const bf16* dn = dy + static_cast<int64_t>(n) * HW * C + c0;
+      for (int q = q0 + py; q < q1; q += kUnroll * PY) {
+        uint4 rx[kUnroll], rd[kUnroll];
 #pragma unroll
-      for (int u = 0; u < NP; ++u) {
-        if (u == 1 && qb >= q1) break;
+        for (int u = 0; u < kUnroll; ++u) {
+          const int64_t o = static_cast<int64_t>(min(q + u * PY, q1 - 1)) * C;
+          rx[u] = *reinterpret_cast<const uint4*>(xn + o);
+          rd[u] = *reinterpret_cast<const uint4*>(dn + o);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (q + u * PY >= q1) break;
+          float v[8], gr[8];
+          cvt8(rx[u], v);
+          cvt8(rd[u], gr);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (v[i] - m[i]) * is[i];
+            if (relu && !(xh * g[i] + b[i] > 0.f)) gr[i] = 0.f;
+            acc[0][i] += gr[i];
+            acc[1][i] = fmaf(gr[i], xh, acc[1][i]);
+          }
+        }
+      }
+    } else {
+      for (int q = q0 + py; q < q1; q += PY) {
+        float xh[8], gr[8];
+        bn_grad8(x, dy, m, is, g, b, n, q / W, q % W, c0, H, W, C, relu, up, xh, gr);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          acc[0][i] += gr[u][i];
-          acc[1][i] = fmaf(gr[u][i], xh[u][i], acc[1][i]);
+          acc[0][i] += gr[i];
+          acc[1][i] = fmaf(gr[i], xh[i], acc[1][i]);
         }
       }
     }
@@ -277,7 +300,7 @@ bn_bwd_reduce_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy
 }
 
 // dx = invstd * (gain * g - m1 - xhat * m2)      grid: (pixel slabs, n); per-channel parameters in registers
-template <bool kTwo>
+template <bool kPlain>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -298,19 +321,40 @@ bn_bwd_apply_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
   ldf8(m1 + c0, a1);
   ldf8(m2 + c0, a2);
   bf16* dxn = dx + static_cast<int64_t>(n) * HW * C + c0;
-  constexpr int NP = kTwo ? 2 : 1;
-  for (int q = q0 + py; q < q1; q += NP * PY) {
-    float xh[NP][8], gr[NP][8];
-    const int qb = q + PY;
-    bn_grad8(x, dy, m, is, g, b, n, q / W, q % W, c0, H, W, C, relu, up, xh[0], gr[0]);
-    if (kTwo && qb < q1) bn_grad8(x, dy, m, is, g, b, n, qb / W, qb % W, c0, H, W, C, relu, up, xh[NP - 1], gr[NP - 1]);
+  if constexpr (kPlain) {
+    const bf16* xn = x + static_cast<int64_t>(n) * HW * C + c0;
+    const bf16* dn = dy + static_cast<int64_t>(n) * HW * C + c0;
+    for (int q = q0 + py; q < q1; q += kUnroll * PY) {
+      uint4 rx[kUnroll], rd[kUnroll];
 #pragma unroll
-    for (int u = 0; u < NP; ++u) {
-      if (u == 1 && qb >= q1) break;
-      float o[8];
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t o = static_cast<int64_t>(min(q + u * PY, q1 - 1)) * C;
+        rx[u] = *reinterpret_cast<const uint4*>(xn + o);
+        rd[u] = *reinterpret_cast<const uint4*>(dn + o);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = is[i] * (g[i] * gr[u][i] - a1[i] - xh[u][i] * a2[i]);
-      st8(dxn + static_cast<int64_t>(u ? qb : q) * C, o);
+      for (int u = 0; u < kUnroll; ++u) {
+        const int qq = q + u * PY;
+        if (qq >= q1) break;
+        float v[8], gr[8], o[8];
+        cvt8(rx[u], v);
+        cvt8(rd[u], gr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (v[i] - m[i]) * is[i];
+          if (relu && !(xh * g[i] + b[i] > 0.f)) gr[i] = 0.f;
+          o[i] = is[i] * (g[i] * gr[i] - a1[i] - xh * a2[i]);
+        }
+        st8(dxn + static_cast<int64_t>(qq) * C, o);
+      }
+    }
+  } else {
+    for (int q = q0 + py; q < q1; q += PY) {
+      float xh[8], gr[8], o[8];
+      bn_grad8(x, dy, m, is, g, b, n, q / W, q % W, c0, H, W, C, relu, up, xh, gr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = is[i] * (g[i] * gr[i] - a1[i] - xh[i] * a2[i]);
+      st8(dxn + static_cast<int64_t>(q) * C, o);
     }
   }
 }

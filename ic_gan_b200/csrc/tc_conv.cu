@@ -92,6 +92,12 @@ __device__ __forceinline__ void load8(const void* base, int64_t elem_off, int is
     v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 }
+// 32-byte (one full L2 sector) store; `p` must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 __device__ __forceinline__ void store8(void* base, int64_t elem_off, int is_bf16, const float (&v)[8]) {
   if (is_bf16) {
     uint4 raw;
@@ -100,9 +106,10 @@ __device__ __forceinline__ void store8(void* base, int64_t elem_off, int is_bf16
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + elem_off) = raw;
   } else {
-    float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + elem_off);
-    p[0] = make_float4(v[0], v[1], v[2], v[3]);
-    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i]);
+    st_global_256(static_cast<float*>(base) + elem_off, w);  // 8 floats, 32-byte aligned (offsets are multiples of 8)
   }
 }
 
@@ -153,43 +160,64 @@ __device__ __forceinline__ void epilogue_block(const EpiArgs& e, uint32_t taddr,
     }
   }
   tmem_ld_wait();
+  const bool wide = e.out_bf16 && (e.Cout % 16 == 0);  // 16 bf16 channels = one full 32-byte sector per store
 #pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    if (!on[g]) continue;
-    float v[8];
+  for (int gp = 0; gp < NG / 2; ++gp) {
+    float v[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = e.alpha * __uint_as_float(r[8 * g + j]);
-    if (e.bias) {
-      v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
-      v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
-    }
-    if (e.res) {
-      if (e.res_bf16) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[2 * g]);
+    for (int hh = 0; hh < 2; ++hh) {
+      const int g = 2 * gp + hh;
+      if (!on[g]) continue;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h[i]);
-          v[2 * i] += f.x;
-          v[2 * i + 1] += f.y;
-        }
-      } else {
-        const float* f0 = reinterpret_cast<const float*>(&rv[2 * g]);
-        const float* f1 = reinterpret_cast<const float*>(&rv[2 * g + 1]);
+      for (int j = 0; j < 8; ++j) v[hh][j] = e.alpha * __uint_as_float(r[8 * g + j]);
+      if (e.bias) {
+        v[hh][0] += bv[2 * g].x; v[hh][1] += bv[2 * g].y; v[hh][2] += bv[2 * g].z; v[hh][3] += bv[2 * g].w;
+        v[hh][4] += bv[2 * g + 1].x; v[hh][5] += bv[2 * g + 1].y; v[hh][6] += bv[2 * g + 1].z; v[hh][7] += bv[2 * g + 1].w;
+      }
+      if (e.res) {
+        if (e.res_bf16) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[2 * g]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[i] += f0[i];
-          v[4 + i] += f1[i];
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            v[hh][2 * i] += f.x;
+            v[hh][2 * i + 1] += f.y;
+          }
+        } else {
+          const float* f0 = reinterpret_cast<const float*>(&rv[2 * g]);
+          const float* f1 = reinterpret_cast<const float*>(&rv[2 * g + 1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[hh][i] += f0[i];
+            v[hh][4 + i] += f1[i];
+          }
         }
       }
-    }
-    if (e.act == ICGAN_ACT_RELU) {
+      if (e.act == ICGAN_ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if (e.act == ICGAN_ACT_TANH) {
+        for (int j = 0; j < 8; ++j) v[hh][j] = fmaxf(v[hh][j], 0.f);
+      } else if (e.act == ICGAN_ACT_TANH) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+        for (int j = 0; j < 8; ++j) v[hh][j] = tanhf(v[hh][j]);
+      }
     }
-    store8(e.y, pix * e.Cout + co0 + 8 * g, e.out_bf16, v);
+    const int64_t off = pix * e.Cout + co0 + 16 * gp;
+    if (wide) {
+      if (on[2 * gp]) {  // Cout % 16 == 0: both halves are in range together
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0][2 * i], v[0][2 * i + 1]);
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(v[1][2 * i], v[1][2 * i + 1]);
+          w[i] = *reinterpret_cast<const uint32_t*>(&lo);
+          w[4 + i] = *reinterpret_cast<const uint32_t*>(&hi);
+        }
+        st_global_256(static_cast<__nv_bfloat16*>(e.y) + off, w);
+      }
+    } else {
+      if (on[2 * gp]) store8(e.y, off, e.out_bf16, v[0]);
+      if (on[2 * gp + 1]) store8(e.y, off + 8, e.out_bf16, v[1]);
+    }
   }
 }
 
