@@ -94,60 +94,89 @@ __global__ void sn_finish_kernel(const IcganSnLayer* layers, float eps, int upda
   }
 }
 
+// The three kernels below move weights between the OIHW float32 master ([Cout][Cin][k][k]) and the kernel layouts
+// ([Cout][k][k][Cin] forward, [Cin][k'][k'][Cout] flipped for dgrad).  A block owns a 32 (co) x 32 (ci) x k*k tile and
+// goes through shared memory, so that global reads and writes are contiguous runs on BOTH sides (the one-element-
+// per-thread version wrote 2-byte elements Cin apart and ran at ~2 % of the HBM roofline).
+static constexpr int kSnTile = 32;
+static constexpr int kSnRow = kSnTile * 9 + 1;  // padded row: k*k <= 9
+
 // OIHW float32 master -> scaled operand copies. fwd: [Cout][kh][kw][Cin]; dgrad: [Cin][k-1-kh][k-1-kw][Cout].
 template <typename TO>
-__global__ void sn_prepare_kernel(const float* __restrict__ W, const float* __restrict__ inv_sigma,
-                                  TO* __restrict__ fwd, TO* __restrict__ dgrad, int Cout, int Cin, int k) {
-  const int64_t total = static_cast<int64_t>(Cout) * Cin * k * k;
+__global__ void __launch_bounds__(256)
+sn_prepare_kernel(const float* __restrict__ W, const float* __restrict__ inv_sigma, TO* __restrict__ fwd,
+                  TO* __restrict__ dgrad, int Cout, int Cin, int k) {
+  __shared__ float sm[kSnTile][kSnRow];
+  const int kk = k * k, ci0 = blockIdx.x * kSnTile, co0 = blockIdx.y * kSnTile;
+  const int nci = min(kSnTile, Cin - ci0), nco = min(kSnTile, Cout - co0);
+  const int rowlen = nci * kk;
   const float sc = inv_sigma ? *inv_sigma : 1.f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int kw = static_cast<int>(i % k);
-    const int kh = static_cast<int>((i / k) % k);
-    const int ci = static_cast<int>((i / (k * k)) % Cin);
-    const int co = static_cast<int>(i / (static_cast<int64_t>(k) * k * Cin));
-    const float v = W[i] * sc;
-    if (fwd) st_from_float(fwd, ((static_cast<int64_t>(co) * k + kh) * k + kw) * Cin + ci, v);
-    if (dgrad) st_from_float(dgrad, ((static_cast<int64_t>(ci) * k + (k - 1 - kh)) * k + (k - 1 - kw)) * Cout + co, v);
+  for (int idx = threadIdx.x; idx < nco * rowlen; idx += blockDim.x) {
+    const int co_l = idx / rowlen, r = idx - co_l * rowlen;
+    sm[co_l][r] = W[(static_cast<int64_t>(co0 + co_l) * Cin + ci0) * kk + r] * sc;
+  }
+  __syncthreads();
+  if (fwd) {
+    for (int idx = threadIdx.x; idx < nco * kk * kSnTile; idx += blockDim.x) {
+      const int ci_l = idx % kSnTile, tap = (idx / kSnTile) % kk, co_l = idx / (kSnTile * kk);
+      if (ci_l < nci)
+        st_from_float(fwd, (static_cast<int64_t>(co0 + co_l) * kk + tap) * Cin + ci0 + ci_l, sm[co_l][ci_l * kk + tap]);
+    }
+  }
+  if (dgrad) {
+    for (int idx = threadIdx.x; idx < nci * kk * kSnTile; idx += blockDim.x) {
+      const int co_l = idx % kSnTile, tap = (idx / kSnTile) % kk, ci_l = idx / (kSnTile * kk);
+      if (co_l < nco)
+        st_from_float(dgrad, (static_cast<int64_t>(ci0 + ci_l) * kk + (kk - 1 - tap)) * Cout + co0 + co_l,
+                      sm[co_l][ci_l * kk + tap]);
+    }
   }
 }
 
 // scratch[0] += <G, W> with G in kernel layout [Cout][k][k][Cin] and W in OIHW
-__global__ void sn_grad_dot_kernel(const float* __restrict__ G, const float* __restrict__ W, float* scratch, int Cout,
-                                   int Cin, int k) {
+__global__ void __launch_bounds__(256)
+sn_grad_dot_kernel(const float* __restrict__ G, const float* __restrict__ W, float* scratch, int Cout, int Cin, int k) {
+  __shared__ float sm[kSnTile][kSnRow];
   __shared__ float sh[8];
-  const int64_t total = static_cast<int64_t>(Cout) * Cin * k * k;
+  const int kk = k * k, ci0 = blockIdx.x * kSnTile, co0 = blockIdx.y * kSnTile;
+  const int nci = min(kSnTile, Cin - ci0), nco = min(kSnTile, Cout - co0);
+  const int rowlen = nci * kk;
+  for (int idx = threadIdx.x; idx < nco * rowlen; idx += blockDim.x) {
+    const int co_l = idx / rowlen, r = idx - co_l * rowlen;
+    sm[co_l][r] = W[(static_cast<int64_t>(co0 + co_l) * Cin + ci0) * kk + r];
+  }
+  __syncthreads();
   float s = 0.f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int kw = static_cast<int>(i % k);
-    const int kh = static_cast<int>((i / k) % k);
-    const int ci = static_cast<int>((i / (k * k)) % Cin);
-    const int64_t co = i / (static_cast<int64_t>(k) * k * Cin);
-    s = fmaf(G[((co * k + kh) * k + kw) * Cin + ci], W[i], s);
+  for (int idx = threadIdx.x; idx < nco * kk * kSnTile; idx += blockDim.x) {
+    const int ci_l = idx % kSnTile, tap = (idx / kSnTile) % kk, co_l = idx / (kSnTile * kk);
+    if (ci_l < nci)
+      s = fmaf(G[(static_cast<int64_t>(co0 + co_l) * kk + tap) * Cin + ci0 + ci_l], sm[co_l][ci_l * kk + tap], s);
   }
   const float t = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(scratch, t);
 }
 
 // dW[i] = (G[map(i)] - (<G,W>/sigma) * u'[row] * v[col] / sigma ... ) see header; without SN: plain relayout
-__global__ void sn_grad_apply_kernel(const float* __restrict__ G, const float* __restrict__ u_new,
-                                     const float* __restrict__ v, const float* __restrict__ sigma,
-                                     const float* __restrict__ scratch, float* __restrict__ dW, int Cout, int Cin,
-                                     int k) {
-  const int64_t total = static_cast<int64_t>(Cout) * Cin * k * k;
-  const int64_t cols = static_cast<int64_t>(Cin) * k * k;
+__global__ void __launch_bounds__(256)
+sn_grad_apply_kernel(const float* __restrict__ G, const float* __restrict__ u_new, const float* __restrict__ v,
+                     const float* __restrict__ sigma, const float* __restrict__ scratch, float* __restrict__ dW,
+                     int Cout, int Cin, int k) {
+  __shared__ float sm[kSnTile][kSnRow];
+  const int kk = k * k, ci0 = blockIdx.x * kSnTile, co0 = blockIdx.y * kSnTile;
+  const int nci = min(kSnTile, Cin - ci0), nco = min(kSnTile, Cout - co0);
+  const int rowlen = nci * kk;
   const float inv = sigma ? sigma[1] : 1.f;
   const float coef = sigma ? scratch[0] * inv : 0.f;  // <G, W> / sigma = <G, W~>
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int kw = static_cast<int>(i % k);
-    const int kh = static_cast<int>((i / k) % k);
-    const int ci = static_cast<int>((i / (k * k)) % Cin);
-    const int64_t co = i / cols;
-    float g = G[((co * k + kh) * k + kw) * Cin + ci];
-    if (sigma) g = (g - coef * u_new[co] * v[i % cols]) * inv;
-    dW[i] = g;
+  for (int idx = threadIdx.x; idx < nco * kk * kSnTile; idx += blockDim.x) {
+    const int ci_l = idx % kSnTile, tap = (idx / kSnTile) % kk, co_l = idx / (kSnTile * kk);
+    if (ci_l < nci) sm[co_l][ci_l * kk + tap] = G[(static_cast<int64_t>(co0 + co_l) * kk + tap) * Cin + ci0 + ci_l];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nco * rowlen; idx += blockDim.x) {
+    const int co_l = idx / rowlen, r = idx - co_l * rowlen;
+    float g = sm[co_l][r];
+    if (sigma) g = (g - coef * u_new[co0 + co_l] * v[static_cast<int64_t>(ci0) * kk + r]) * inv;
+    dW[(static_cast<int64_t>(co0 + co_l) * Cin + ci0) * kk + r] = g;
   }
 }
 
@@ -172,9 +201,9 @@ extern "C" int icgan_sn_power_iteration(const IcganSnLayer* layers_dev, int n_la
 extern "C" int icgan_sn_prepare_weight(const float* W, const float* inv_sigma_dev, void* wk_fwd, void* wk_dgrad,
                                        int Cout, int Cin, int ksize, int out_dtype, void* stream) {
   ICGAN_REQUIRE(W && (wk_fwd || wk_dgrad), "icgan_sn_prepare_weight: null pointer");
-  const int64_t total = static_cast<int64_t>(Cout) * Cin * ksize * ksize;
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  ICGAN_REQUIRE(ksize >= 1 && ksize <= 3, "icgan_sn_prepare_weight: ksize must be 1..3 (got %d)", ksize);
+  const dim3 blocks(static_cast<unsigned>(ceil_div(Cin, kSnTile)), static_cast<unsigned>(ceil_div(Cout, kSnTile)));
+  ICGAN_REQUIRE(blocks.y <= 65535u, "icgan_sn_prepare_weight: Cout too large");
   if (out_dtype == ICGAN_BF16)
     sn_prepare_kernel<__nv_bfloat16><<<blocks, 256, 0, STREAM>>>(W, inv_sigma_dev, static_cast<__nv_bfloat16*>(wk_fwd),
                                                                 static_cast<__nv_bfloat16*>(wk_dgrad), Cout, Cin, ksize);
@@ -189,9 +218,9 @@ extern "C" int icgan_sn_weight_grad(const float* G_k, const float* W, const floa
                                     const float* sigma, float* scratch, float* dW, int Cout, int Cin, int ksize,
                                     void* stream) {
   ICGAN_REQUIRE(G_k && dW, "icgan_sn_weight_grad: null pointer");
-  const int64_t total = static_cast<int64_t>(Cout) * Cin * ksize * ksize;
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  ICGAN_REQUIRE(ksize >= 1 && ksize <= 3, "icgan_sn_weight_grad: ksize must be 1..3 (got %d)", ksize);
+  const dim3 blocks(static_cast<unsigned>(ceil_div(Cin, kSnTile)), static_cast<unsigned>(ceil_div(Cout, kSnTile)));
+  ICGAN_REQUIRE(blocks.y <= 65535u, "icgan_sn_weight_grad: Cout too large");
   if (sigma) {
     ICGAN_REQUIRE(W && u_new && v && scratch, "icgan_sn_weight_grad: spectral-norm buffers missing");
     ICGAN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), STREAM));

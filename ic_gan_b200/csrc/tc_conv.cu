@@ -805,6 +805,176 @@ static int choose_splits(int items, int k_chunks) {
   return best;
 }
 
+// ------------------------------------------------------------------------------------------------ RGB-side input
+// tc_conv_rgb_kernel: k x k convolution of a <= 3-channel image (k*k*Cs <= 32, the first layer of D,
+// BigGAN.py:491 with DBlock conv1).  The reduction is only 27 long, so the layer is bound by writing its output; an
+// explicit im2col buffer (32 bf16 per pixel) cost more traffic than the result.  Here four builder warps gather each
+// pixel's 27 inputs and write the 128 x 32 bf16 A tile straight into shared memory in the UMMA K-major/64-byte-swizzle
+// layout (16-byte chunk c of row r lands at chunk c ^ ((r >> 1) & 3)), the weights sit in shared memory for the whole
+// kernel, one elected lane issues the two K=16 UMMAs of a tile, and eight epilogue warps stream the result out.
+struct TcRgbParams {
+  int B, H, W, Cs, ksz, Cout, BN;
+  int64_t P;
+  int total_tiles;
+  uint32_t idesc;
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* wcol;  // [Cout][32], column j = tap * Cs + ci
+  int out_bf16, act;
+  void* y;
+  const float* bias;
+  const float* alpha;
+};
+static constexpr int kRgbThreads = 13 * 32;  // 4 builder warps, 1 MMA warp, 8 epilogue warps
+static constexpr int kRgbBufs = 4;
+
+// KSZ / CS > 0: compile-time filter size and channel count (the gather unrolls into registers); 0 = run-time values.
+template <int KSZ, int CS>
+__global__ void __launch_bounds__(kRgbThreads, 1)
+tc_conv_rgb_kernel(const TcRgbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* sA = smem;                                  // kRgbBufs x 128 rows x 64 bytes
+  uint8_t* sB = smem + kRgbBufs * 8192;                // 256 rows x 64 bytes
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + 256 * 64);
+  uint64_t* a_empty = a_full + kRgbBufs;
+  uint64_t* tfull = a_empty + kRgbBufs;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRgbBufs; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  // weights -> shared memory (swizzled K-major rows of 64 bytes; rows >= Cout are zero)
+  for (int idx = threadIdx.x; idx < p.BN * 4; idx += blockDim.x) {
+    const int r = idx >> 2, c = idx & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < p.Cout) v = *reinterpret_cast<const uint4*>(p.wcol + static_cast<int64_t>(r) * 32 + c * 8);
+    *reinterpret_cast<uint4*>(sB + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = v;
+  }
+  fence_proxy_async();
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== builders: thread t owns row t of the A tile =====================
+    const int r = threadIdx.x;
+    const int ksz = KSZ > 0 ? KSZ : p.ksz, cs = CS > 0 ? CS : p.Cs;
+    const int pad = ksz >> 1;
+    int buf = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int64_t pix = static_cast<int64_t>(tile) * 128 + r;
+      __nv_bfloat16 v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float2bfloat16_rn(0.f);
+      if (pix < p.P) {
+        const int w = static_cast<int>(pix % p.W);
+        const int h = static_cast<int>((pix / p.W) % p.H);
+        const int64_t n = pix / (static_cast<int64_t>(p.H) * p.W);
+#pragma unroll
+        for (int kh = 0; kh < (KSZ > 0 ? KSZ : 3); ++kh) {
+          if (kh >= ksz) break;
+          const int ih = h + kh - pad;
+#pragma unroll
+          for (int kw = 0; kw < (KSZ > 0 ? KSZ : 3); ++kw) {
+            if (kw >= ksz) break;
+            const int iw = w + kw - pad;
+            const bool in = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+            const __nv_bfloat16* src = p.x + ((n * p.H + ih) * p.W + iw) * cs;
+#pragma unroll
+            for (int ci = 0; ci < (CS > 0 ? CS : 3); ++ci) {
+              if (ci >= cs) break;
+              const int j = (kh * ksz + kw) * cs + ci;
+              if (in) v[j] = src[ci];
+            }
+          }
+        }
+      }
+      mbar_wait(&a_empty[buf], phase ^ 1u);
+      uint8_t* row = sA + buf * 8192 + r * 64;
+      const uint4* vv = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ ((r >> 1) & 3)) << 4)) = vv[c];
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&a_full[buf]);
+      if (++buf == kRgbBufs) {
+        buf = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    int buf = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint64_t desc0 = umma_desc_kmajor(0, 64);
+    const uint64_t db = desc0 + (((base + kRgbBufs * 8192u) & 0x3FFFFu) >> 4);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      mbar_wait(&a_full[buf], phase);
+      tc_fence_after();
+      const uint64_t da = desc0 + (((base + static_cast<uint32_t>(buf) * 8192u) & 0x3FFFFu) >> 4);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+      if (elect_one_sync()) {
+        umma_bf16(d_tmem, da, db, p.idesc, 0u);
+        umma_bf16(d_tmem, da + 2u, db + 2u, p.idesc, 1u);
+        umma_commit(&a_empty[buf]);
+        umma_commit(&tfull[acc]);
+      }
+      __syncwarp();
+      if (++buf == kRgbBufs) {
+        buf = 0;
+        phase ^= 1u;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ===================== epilogue: 8 warps, two per TMEM lane quadrant =====================
+    const int q = warp & 3;
+    const int grp = (warp - 5) >> 2;
+    const float alpha = p.alpha ? *p.alpha : 1.f;
+    const EpiArgs ea{p.y, p.bias, nullptr, p.Cout, p.out_bf16, 0, p.act, alpha};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int64_t pix = static_cast<int64_t>(tile) * 128 + q * 32 + lane;
+      const bool valid = pix < p.P;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u;
+      int c = 0, blk = 0;
+      for (; c + 32 <= p.BN; c += 32, ++blk)
+        if ((blk & 1) == grp) epilogue_block<32>(ea, taddr + static_cast<uint32_t>(c), c, pix, pix, valid);
+      if (c < p.BN && (blk & 1) == grp) epilogue_block<16>(ea, taddr + static_cast<uint32_t>(c), c, pix, pix, valid);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci], operands read straight from the NHWC tensors:
 // the reduction index (pixels) is the ROW of each TMA box and channels are contiguous, i.e. both UMMA operands are
@@ -1318,6 +1488,42 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (bn_stats) tc_conv_kernel<4><<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   else tc_conv_kernel<8><<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_conv2d_rgb_tc(const void* x, const void* wcol, const float* alpha_dev, const float* bias, void* y,
+                                   int B, int H, int W, int Cs, int Cout, int ksize, int out_dtype, int act,
+                                   void* stream) {
+  ICGAN_REQUIRE(x && wcol && y, "icgan_conv2d_rgb_tc: null pointer");
+  ICGAN_REQUIRE(B > 0 && H > 0 && W > 0 && Cs > 0, "icgan_conv2d_rgb_tc: bad shape");
+  ICGAN_REQUIRE((ksize == 1 || ksize == 3) && ksize * ksize * Cs <= 32,
+                "icgan_conv2d_rgb_tc: needs k*k*Cs <= 32 (got k=%d Cs=%d)", ksize, Cs);
+  ICGAN_REQUIRE(Cout % 8 == 0 && Cout >= 8 && Cout <= 256, "icgan_conv2d_rgb_tc: Cout must be a multiple of 8 in [8, 256]");
+  TcRgbParams p{};
+  p.B = B; p.H = H; p.W = W; p.Cs = Cs; p.ksz = ksize; p.Cout = Cout;
+  p.BN = (Cout + 15) / 16 * 16;
+  p.P = static_cast<int64_t>(B) * H * W;
+  p.total_tiles = static_cast<int>((p.P + 127) / 128);
+  p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.BN));
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.wcol = static_cast<const __nv_bfloat16*>(wcol);
+  p.out_bf16 = out_dtype == ICGAN_BF16;
+  p.act = act;
+  p.y = y; p.bias = bias; p.alpha = alpha_dev;
+  const uint32_t smem_bytes = 1024u + kRgbBufs * 8192u + 256u * 64u + 512u;
+  ICGAN_REQUIRE(Cs <= 3, "icgan_conv2d_rgb_tc: at most 3 input channels (got %d)", Cs);
+  static bool configured = false;
+  if (!configured) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_rgb_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_rgb_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (ksize == 3 && Cs == 3)
+    tc_conv_rgb_kernel<3, 3><<<grid, kRgbThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    tc_conv_rgb_kernel<0, 0><<<grid, kRgbThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }

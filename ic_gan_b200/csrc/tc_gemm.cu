@@ -18,7 +18,7 @@ namespace icgan {
 namespace {
 
 constexpr int kStagesMax = 8;
-constexpr int kThreadsG = 192;
+constexpr int kThreadsG = 320;  // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quadrant)
 constexpr uint32_t kSmemBudgetG = 227u * 1024u;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -70,12 +70,18 @@ struct GemmTcParams {
   int m_tiles, n_tiles, total_tiles, k_iters, BN, b_boxes, stages;
   uint32_t a_bytes, b_tx, stage_bytes, idesc;
   int64_t ldc, scb;
-  int out_bf16;
+  int out_bf16, c16, c8;  // bf16 (f32) output is 32-byte aligned at every multiple of 16 (8) columns
   float alpha;
   void* C;
 };
 
 constexpr int kKC = 64;  // reduction extent per pipeline stage
+
+__device__ __forceinline__ void st256(void* ptr, const uint32_t (&w)[8]) {  // one full 32-byte sector
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 
 __global__ void __launch_bounds__(kThreadsG, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -98,7 +104,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_barrier_init();
   }
@@ -184,6 +190,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 32-column blocks
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -194,28 +201,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u;
       const int64_t coff = static_cast<int64_t>(b) * p.scb + static_cast<int64_t>(m) * p.ldc;
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + static_cast<uint32_t>(c), r);
+      int blk = 0;
+      for (int c = 0; c < p.BN; c += 32, ++blk) {
+        if ((blk & 1) != grp) continue;
+        __syncwarp();
+        uint32_t r[32];
+        if (c + 32 <= p.BN) {
+          tmem_ld32(taddr + static_cast<uint32_t>(c), r);
+        } else {  // BN is a multiple of 16: last half block
+          uint32_t r16[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(c), r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = r16[j];
+        }
         tmem_ld_wait();
+        const int ncols = c + 32 <= p.BN ? 32 : 16;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int n = n0 + c + half * 8;
-          if (m < p.M && n < p.N) {
-            if (p.out_bf16) {
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+        for (int gp = 0; gp < 2; ++gp) {  // pairs of 8-column groups
+          const int n = n0 + c + gp * 16;
+          if (m >= p.M || gp * 16 >= ncols || n >= p.N) break;
+          const bool second = n + 8 < p.N;  // N is a multiple of 8
+          if (!p.out_bf16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                h[j] = __floats2bfloat162_rn(p.alpha * __uint_as_float(r[half * 8 + 2 * j]),
-                                             p.alpha * __uint_as_float(r[half * 8 + 2 * j + 1]));
-              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + coff + n) = pk;
+            for (int hh = 0; hh < 2; ++hh) {
+              if (hh == 1 && !second) break;
+              float* dst = static_cast<float*>(p.C) + coff + n + hh * 8;
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(p.alpha * __uint_as_float(r[gp * 16 + hh * 8 + j]));
+              if (p.c8) {  // 8 floats = one 32-byte sector
+                st256(dst, w);
+              } else {
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              }
+            }
+          } else {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(p.alpha * __uint_as_float(r[gp * 16 + 2 * j]),
+                                                             p.alpha * __uint_as_float(r[gp * 16 + 2 * j + 1]));
+              w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + coff + n;
+            if (p.c16 && second) {  // 16 bf16 = one sector
+              st256(dst, w);
             } else {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + coff + n);
-              dst[0] = make_float4(p.alpha * __uint_as_float(r[half * 8 + 0]), p.alpha * __uint_as_float(r[half * 8 + 1]),
-                                   p.alpha * __uint_as_float(r[half * 8 + 2]), p.alpha * __uint_as_float(r[half * 8 + 3]));
-              dst[1] = make_float4(p.alpha * __uint_as_float(r[half * 8 + 4]), p.alpha * __uint_as_float(r[half * 8 + 5]),
-                                   p.alpha * __uint_as_float(r[half * 8 + 6]), p.alpha * __uint_as_float(r[half * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+              if (second) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
             }
           }
         }
@@ -266,6 +300,8 @@ extern "C" int icgan_gemm_tc(const void* A, const void* B, void* C, int M, int N
   p.stages = stages;
   p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.BN)) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
   p.ldc = ldc; p.scb = scb; p.out_bf16 = c_dtype == ICGAN_BF16; p.alpha = alpha; p.C = C;
+  p.c16 = (ldc % 16 == 0) && (scb % 16 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0);
+  p.c8 = (scb % 8 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0);
 
   CUtensorMap tmA, tmB;
   int rc;

@@ -143,6 +143,12 @@ class SNState:
             return
         self.version = stamp
         co, ci, k, _ = w.shape
+        if self.mode == "tc" and self.mode_d == "tc":  # both operands are plain bf16 relayouts: write them directly
+            self.wk_fwd = torch.empty(co, k, k, ci, device=w.device, dtype=torch.bfloat16)
+            self.wk_dgrad = torch.empty(ci, k, k, co, device=w.device, dtype=torch.bfloat16)
+            call("icgan_sn_prepare_weight", ptr(w), None, ptr(self.wk_fwd), ptr(self.wk_dgrad), co, ci, k, L.BF16,
+                 stream_ptr())
+            return
         f32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32)
         d32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32)
         call("icgan_sn_prepare_weight", ptr(w), None, ptr(f32), ptr(d32), co, ci, k, L.F32, stream_ptr())
@@ -221,6 +227,14 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
     if mode == "tc":
         y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
         _tc_conv(x, wk, st.alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act, stats)
+        return y
+    if mode == "col" and kp == 32 and cin <= 3 and cout <= 256 and residual is None and x.dtype == torch.bfloat16:
+        # RGB-side input, im2col fused into the kernel; the backward rebuilds the column buffer only if it needs it
+        y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
+        _SHAPE[0] = (B, H, W, cin, cout, k)
+        _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
+               lambda: call("icgan_conv2d_rgb_tc", ptr(x), ptr(wk), ptr(st.alpha), ptr(bias), ptr(y), B, H, W, cin, cout, k,
+                            dt(y), act, stream_ptr()))
         return y
     if mode == "col":  # RGB-side input: im2col (27 -> 32 columns) + tensor-core 1x1
         xcol = _im2col(x, k, kp)
@@ -561,6 +575,7 @@ class ScaleAddFn(torch.autograd.Function):
 
 
 def _gemm_tc(A, B_, Cm, M, N, K, batch, a_mn, b_mn, lda, sab, ldb, sbb, ldc, scb, alpha=1.0):
+    _SHAPE[0] = ("gemm", batch, M, N, K)
     _timed("tc_gemm_kernel", 2.0 * batch * M * N * K,
            lambda: call("icgan_gemm_tc", ptr(A), ptr(B_), ptr(Cm), M, N, K, batch, int(a_mn), int(b_mn), lda, sab, ldb,
                         sbb, ldc, scb, float(alpha), dt(Cm), stream_ptr()))

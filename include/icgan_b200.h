@@ -51,6 +51,13 @@ int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha_dev, const
                     void* y, float* bn_stats, int B, int H, int W, int Cin, int Cout, int ksize, int out_dtype,
                     int res_dtype, int res_shift, int act, void* stream);
 
+/* RGB-side input convolution on the tensor cores with the im2col fused into the kernel (the first conv of D,
+ * BigGAN_PyTorch/BigGAN.py:491-495 -> layers.py DBlock.conv1; replaces F.conv2d on a 3-channel image):
+ *   y[n,h,w,co] = act(alpha * sum_{kh,kw,ci} x[n,h+kh-p,w+kw-p,ci] * wcol[co, (kh*k+kw)*Cs+ci] + bias[co])
+ * x:[B,H,W,Cs] bf16 with Cs<=3 and k*k*Cs<=32; wcol:[Cout,32] bf16 (columns >= k*k*Cs zero); Cout%8==0, Cout<=256. */
+int icgan_conv2d_rgb_tc(const void* x, const void* wcol, const float* alpha_dev, const float* bias, void* y, int B, int H,
+                        int W, int Cs, int Cout, int ksize, int out_dtype, int act, void* stream);
+
 /* Tensor-core weight gradient for 3x3/1x1 stride-1 convs (replaces cudnn_convolution_backward_weight,
  * stylegan2_ada_pytorch/torch_utils/ops/conv2d_gradfix.py:223-227, and ATen's conv backward under BigGAN):
  *   dwk[co,kh,kw,ci] += sum_{n,h,w} dy[n,h,w,co] * x[n,h+kh-p,w+kw-p,ci]

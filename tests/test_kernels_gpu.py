@@ -201,3 +201,28 @@ def test_operand_copies_follow_weight_updates(cuda_device, cdt):
         m(x.to(cdt)).float().pow(2).mean().backward()
         opt.step()
         m.eval()
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 40, 96, 3, 3), (1, 16, 16, 8, 3, 1), (3, 20, 12, 200, 2, 3)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_rgb_input_conv_c_abi(cuda_device, shape, act):
+    """icgan_conv2d_rgb_tc (im2col fused into the tensor-core kernel) against F.conv2d on the same bf16-rounded inputs;
+    pixel counts that are not multiples of the 128-row tile, a Cout tail, ReLU epilogue."""
+    from ic_gan_b200 import _lib as L
+    from ic_gan_b200._lib import call, dt, ptr
+    B, H, W, cout, cs, k = shape
+    torch.manual_seed(1)
+    x = torch.randn(B, cs, H, W, device=cuda_device).to(torch.bfloat16)
+    w = (torch.randn(cout, cs, k, k, device=cuda_device) * 0.3).to(torch.bfloat16)
+    bias = torch.randn(cout, device=cuda_device)
+    alpha = torch.tensor([0.7], device=cuda_device)
+    wcol = torch.zeros(cout, 32, device=cuda_device, dtype=torch.bfloat16)
+    wcol[:, :k * k * cs] = w.permute(0, 2, 3, 1).reshape(cout, -1)
+    xn = _nhwc(x)
+    y = torch.empty(B, H, W, cout, device=cuda_device, dtype=torch.bfloat16)
+    call("icgan_conv2d_rgb_tc", ptr(xn), ptr(wcol), ptr(alpha), ptr(bias), ptr(y), B, H, W, cs, cout, k, dt(y),
+         L.ACT_RELU if act else L.ACT_NONE, torch.cuda.current_stream().cuda_stream)
+    ref = 0.7 * F.conv2d(x.float(), w.float(), None, 1, k // 2) + bias.view(1, -1, 1, 1)
+    if act:
+        ref = torch.relu(ref)
+    _close(y.permute(0, 3, 1, 2), ref, 1e-2, "rgb conv")
