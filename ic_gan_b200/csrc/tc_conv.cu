@@ -724,6 +724,9 @@ static int launch_conv_halo(const void* x, const void* wk, const float* alpha_de
   p.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   if (cw_override && cw_override <= p.cw && Cin % cw_override == 0) p.cw = cw_override;
   // Cin = 96, 160, ...: 64-channel chunks with the last one part out of bounds (TMA zero-fills both operands).
+  // Measured twice, a loss both times: Cout = 96: 932 -> 866 TFLOP/s (the zero K columns cost MMA time); the 96 -> 3
+  // image conv (Cout padded to 8, pure A traffic): 16.6 -> 22.4 ms per step -- boxes that are half out of bounds move
+  // slower than the narrower 64-byte-row boxes they replace.  Kept as an experiment switch only.
   static const int pad64 = env_int("ICGAN_TC_HALO_PAD64", 0);
   if (pad64 && p.cw < 64 && Cin > 64) p.cw = 64;
   p.swz = static_cast<uint32_t>(p.cw * 2);
@@ -874,50 +877,72 @@ tc_conv_rgb_kernel(const TcRgbParams p) {
 
   if (warp < 4) {
     // ===================== builders: thread t owns row t of the A tile =====================
+    // The gathers of the next two tiles are in flight while a tile is packed and published (nothing else would hide
+    // their L2/HBM latency: a builder warp has its scheduler to itself).
     const int r = threadIdx.x;
     const int ksz = KSZ > 0 ? KSZ : p.ksz, cs = CS > 0 ? CS : p.Cs;
     const int pad = ksz >> 1;
-    int buf = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    constexpr int NV = (KSZ > 0 && CS > 0) ? KSZ * KSZ * CS : 32;
+    auto gather = [&](int tile, unsigned short (&rv)[NV]) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) rv[j] = 0;
       const int64_t pix = static_cast<int64_t>(tile) * 128 + r;
-      __nv_bfloat16 v[32];
+      if (tile >= p.total_tiles || pix >= p.P) return;
+      const int w = static_cast<int>(pix % p.W);
+      const int h = static_cast<int>((pix / p.W) % p.H);
+      const int64_t n = pix / (static_cast<int64_t>(p.H) * p.W);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __float2bfloat16_rn(0.f);
-      if (pix < p.P) {
-        const int w = static_cast<int>(pix % p.W);
-        const int h = static_cast<int>((pix / p.W) % p.H);
-        const int64_t n = pix / (static_cast<int64_t>(p.H) * p.W);
+      for (int kh = 0; kh < (KSZ > 0 ? KSZ : 3); ++kh) {
+        if (kh >= ksz) break;
+        const int ih = h + kh - pad;
 #pragma unroll
-        for (int kh = 0; kh < (KSZ > 0 ? KSZ : 3); ++kh) {
-          if (kh >= ksz) break;
-          const int ih = h + kh - pad;
+        for (int kw = 0; kw < (KSZ > 0 ? KSZ : 3); ++kw) {
+          if (kw >= ksz) break;
+          const int iw = w + kw - pad;
+          const bool in = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+          const unsigned short* src = reinterpret_cast<const unsigned short*>(p.x) + ((n * p.H + ih) * p.W + iw) * cs;
 #pragma unroll
-          for (int kw = 0; kw < (KSZ > 0 ? KSZ : 3); ++kw) {
-            if (kw >= ksz) break;
-            const int iw = w + kw - pad;
-            const bool in = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-            const __nv_bfloat16* src = p.x + ((n * p.H + ih) * p.W + iw) * cs;
-#pragma unroll
-            for (int ci = 0; ci < (CS > 0 ? CS : 3); ++ci) {
-              if (ci >= cs) break;
-              const int j = (kh * ksz + kw) * cs + ci;
-              if (in) v[j] = src[ci];
-            }
+          for (int ci = 0; ci < (CS > 0 ? CS : 3); ++ci) {
+            if (ci >= cs) break;
+            if (in) rv[(kh * ksz + kw) * cs + ci] = __ldg(src + ci);
           }
         }
       }
+    };
+    int buf = 0;
+    uint32_t phase = 0;
+    auto publish = [&](const unsigned short (&rv)[NV]) {
+      uint32_t wv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t lo = 2 * i < NV ? rv[2 * i] : 0u, hi = 2 * i + 1 < NV ? rv[2 * i + 1] : 0u;
+        wv[i] = lo | (hi << 16);
+      }
       mbar_wait(&a_empty[buf], phase ^ 1u);
       uint8_t* row = sA + buf * 8192 + r * 64;
-      const uint4* vv = reinterpret_cast<const uint4*>(v);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ ((r >> 1) & 3)) << 4)) = vv[c];
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(row + ((c ^ ((r >> 1) & 3)) << 4)) =
+            make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&a_full[buf]);
       if (++buf == kRgbBufs) {
         buf = 0;
         phase ^= 1u;
       }
+    };
+    unsigned short ra[NV], rb[NV];
+    const int step = static_cast<int>(gridDim.x);
+    int tile = blockIdx.x;
+    gather(tile, ra);
+    gather(tile + step, rb);
+    while (tile < p.total_tiles) {
+      publish(ra);
+      gather(tile + 2 * step, ra);
+      if (tile + step >= p.total_tiles) break;
+      publish(rb);
+      gather(tile + 3 * step, rb);
+      tile += 2 * step;
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
