@@ -354,8 +354,19 @@ def main():
     roofline = None
     if dom:
         ach = per_kernel[dom][0] / per_kernel[dom][1] * 1e-12
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
+        label = {"tc_conv_kernel": "tc_conv_halo_kernel + tc_conv_kernel + tc_conv_rgb_kernel (conv forward and dgrad)",
+                 "tc_wgrad_kernel": "tc_wgrad_kernel + tc_wgrad_halo_kernel"}.get(dom, dom)
+        # DRAM bytes of one representative launch of the dominant kernel from the committed `ncu --set full` capture
+        traffic, traffic_launch = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f).get(dom)
+            if tj:
+                traffic, traffic_launch = tj["dram_bytes_per_launch"], tj["launch"]
+        roofline = {"kernel": label, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"], "traffic": traffic, "traffic_launch": traffic_launch,
+                    "peak_source": pk["source"] + ", sustained",
                     "flops_per_launch": per_kernel[dom][0] / per_kernel[dom][2], "kernels": kinfo}
     f_step = 4 * w["G_f"] + 8 * w["D_f"]  # GF per image, reference step model
     step_tf = f_step * 1e9 * value / world * 1e-12
