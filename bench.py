@@ -130,14 +130,48 @@ def oracle_step_rate(w, batch, steps, warmup, threads):
     return batch / dt, dt
 
 
+ORACLE_THREADS = 16  # per worker process: a batch-1 256x256 step does not scale past ~16-32 threads (measured: 128
+#                      threads in one process = 89.6 s per step on the GPU box's host, 16 threads = ~9 s)
+
+
+def oracle_pool_rate(workload, batch, steps, warmup):
+    """The oracle on ALL host cores: cpu_count // ORACLE_THREADS independent worker processes (independent samples, as the
+    reference's data parallelism would place them), each timing `steps` oracle train_steps at micro-batch `batch`.
+    Returns (aggregate images/s, mean seconds per step, workers, threads per worker)."""
+    import subprocess
+    cores = os.cpu_count() or 1
+    threads = min(ORACLE_THREADS, cores)
+    workers = max(1, cores // threads)
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--oracle-worker", "--workload", workload, "--steps", str(steps),
+           "--warmup", str(warmup), "--cpu-batch", str(batch), "--threads", str(threads)]
+    procs = [subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for _ in range(workers)]
+    dts = []
+    for pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"oracle worker failed: {err[-2000:]}")
+        dts.append(json.loads(out.strip().splitlines()[-1])["dt"])
+    return sum(batch / d for d in dts), sum(dts) / len(dts), workers, threads
+
+
+def run_oracle_worker(args, w):
+    ips, dt = oracle_step_rate(w, args.cpu_batch, args.steps, args.warmup, args.threads)
+    print(json.dumps({"dt": dt, "ips": ips}), flush=True)
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    batch = 2 if (args.steps + args.warmup) <= 6 else 1
-    ips, dt = oracle_step_rate(w, batch, args.steps, args.warmup, threads)
-    sample = f"oracle train_step (CPU restatement of train_fns.py:40-191), micro-batch {batch}, fp32, {threads} threads"
+    batch = 1
+    ips, dt, workers, threads = oracle_pool_rate(args.workload, batch, args.steps, args.warmup)
+    sample = (f"oracle train_step (CPU restatement of train_fns.py:40-191), fp32, {workers} worker processes x {threads} "
+              f"threads, each stepping its own micro-batch of {batch}")
+    threads = workers * threads
     line = {"impl": "reference", "metric": f"{METRIC} {w['resolution']}x{w['resolution']}", "value": ips,
             "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -161,6 +195,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--oracle-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-batch", type=int, default=1, help=argparse.SUPPRESS)
+    ap.add_argument("--threads", type=int, default=ORACLE_THREADS, help=argparse.SUPPRESS)
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: short warm-up allowed, no e2e/cpu legs "
                                                        "(a number printed by such a run is never a bench value)")
     args = ap.parse_args()
@@ -169,6 +206,8 @@ def main():
         w["per_gpu_batch"] = args.per_gpu_batch
     if args.micro_batch:
         w["micro_batch"] = args.micro_batch
+    if args.oracle_worker:
+        return run_oracle_worker(args, w)
     if args.impl == "reference":
         return run_reference(args, w)
     if args.ncu:
@@ -381,12 +420,12 @@ def main():
             "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
         cb = 1 if w["resolution"] >= 256 else 2
-        ips, dt = oracle_step_rate(w, cb, 1, 0, threads)
-        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": f"1 oracle G+D step (CPU restatement of train_fns.py:40-191), micro-batch {cb}, "
-                                          f"fp32, {dt:.1f} s, no warm-up"}
+        ips, dt, workers, threads = oracle_pool_rate(args.workload, cb, 1, 1)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": workers * threads, "kind": "port",
+                                "sample": f"1 warm oracle G+D step (CPU restatement of train_fns.py:40-191) in each of "
+                                          f"{workers} worker processes x {threads} threads, micro-batch {cb}, fp32, "
+                                          f"{dt:.1f} s per step"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
