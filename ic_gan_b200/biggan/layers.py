@@ -85,10 +85,11 @@ class SNConv2d(nn.Conv2d, SN):
             raise NotImplementedError("SNConv2d on B200: square 1x1/3x3 kernels, stride 1, 'same' padding only")
         self._sn_init("conv", num_svs, num_itrs, out_channels, eps)
 
-    def conv_nhwc(self, x, residual=None, res_shift=0, act=ACT_NONE, out_dtype=None, stats=None):
+    def conv_nhwc(self, x, residual=None, res_shift=0, act=ACT_NONE, out_dtype=None, stats=None, mask_input=False,
+                  act_bwd_in_consumer=False):
         st = self._sn_ready()
         return ops.SNConvFn.apply(x, self.weight, self.bias, residual, st, res_shift, act,
-                                  out_dtype if out_dtype is not None else x.dtype, stats)
+                                  out_dtype if out_dtype is not None else x.dtype, stats, mask_input, act_bwd_in_consumer)
 
     def bn_stats_buffer(self, x):
         """float32 [2*Cout] accumulator if this conv can emit the batch statistics of its output from its epilogue
@@ -271,15 +272,17 @@ class DBlock(nn.Module):
 
     def forward_nhwc(self, x):
         down = bool(self.downsample)
-        h = ops.ReluFn.apply(x) if self.preactivation else x
-        h = self.conv1.conv_nhwc(h, act=ACT_RELU)
+        # Both ReLU backwards of the block are done by the consuming conv's dgrad (gate in its epilogue): the
+        # pre-activation ReLU and conv1's fused ReLU pass gradients through unchanged.
+        h = ops.ReluPassFn.apply(x) if self.preactivation else x
+        h = self.conv1.conv_nhwc(h, act=ACT_RELU, mask_input=self.preactivation, act_bwd_in_consumer=True)
         s = ops.Pool2Fn.apply(x, None, 0.25, 0) if down else x
         if self.learnable_sc:
             s = self.conv_sc.conv_nhwc(s)
         if down:
-            h = self.conv2.conv_nhwc(h)
+            h = self.conv2.conv_nhwc(h, mask_input=True)
             return ops.Pool2Fn.apply(h, s, 0.25, 0)
-        return self.conv2.conv_nhwc(h, residual=s)
+        return self.conv2.conv_nhwc(h, residual=s, mask_input=True)
 
     def forward(self, x):
         xin = to_nhwc(x)

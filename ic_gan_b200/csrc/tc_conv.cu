@@ -122,6 +122,7 @@ struct EpiArgs {
   const void* res;
   int Cout, out_bf16, res_bf16, act;
   float alpha;
+  int res_mask;  // 1: `res` is not added but gates the result, y = res > 0 ? y : 0 (ReLU backward fused into dgrad)
 };
 
 template <int NC>
@@ -175,22 +176,30 @@ __device__ __forceinline__ void epilogue_block(const EpiArgs& e, uint32_t taddr,
         v[hh][4] += bv[2 * g + 1].x; v[hh][5] += bv[2 * g + 1].y; v[hh][6] += bv[2 * g + 1].z; v[hh][7] += bv[2 * g + 1].w;
       }
       if (e.res) {
+        float rr[8];
         if (e.res_bf16) {
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[2 * g]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float2 f = __bfloat1622float2(h[i]);
-            v[hh][2 * i] += f.x;
-            v[hh][2 * i + 1] += f.y;
+            rr[2 * i] = f.x;
+            rr[2 * i + 1] = f.y;
           }
         } else {
           const float* f0 = reinterpret_cast<const float*>(&rv[2 * g]);
           const float* f1 = reinterpret_cast<const float*>(&rv[2 * g + 1]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            v[hh][i] += f0[i];
-            v[hh][4 + i] += f1[i];
+            rr[i] = f0[i];
+            rr[4 + i] = f1[i];
           }
+        }
+        if (e.res_mask) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[hh][j] = rr[j] > 0.f ? v[hh][j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[hh][j] += rr[j];
         }
       }
       if (e.act == ICGAN_ACT_RELU) {
@@ -393,7 +402,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;
     const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
     const float alpha = p.alpha ? *p.alpha : 1.f;
-    const EpiArgs ea{p.y, p.bias, p.res, p.Cout, p.out_bf16, p.res_bf16, p.act, alpha};
+    const EpiArgs ea{p.y, p.bias, p.res, p.Cout, p.out_bf16, p.res_bf16, p.act, alpha, p.res_shift == 2};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -402,7 +411,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = (n < p.B) && (h < p.H) && (w < p.W);
       const int64_t pix = (static_cast<int64_t>(n) * p.H + h) * p.W + w;
       int64_t rpix = pix;
-      if (p.res_shift) rpix = (static_cast<int64_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      if (p.res_shift == 1) rpix = (static_cast<int64_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u;
@@ -676,7 +685,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 2) >> 2;
     const int m = half * 128 + q * 32 + lane;
     const float alpha = p.alpha ? *p.alpha : 1.f;
-    const EpiArgs ea{p.y, p.bias, p.res, p.Cout, p.out_bf16, p.res_bf16, p.act, alpha};
+    const EpiArgs ea{p.y, p.bias, p.res, p.Cout, p.out_bf16, p.res_bf16, p.act, alpha, p.res_shift == 2};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -684,7 +693,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int h = t.h0 + (m >> 4), w = t.w0 + (m & 15);
       const int64_t pix = (static_cast<int64_t>(t.n) * p.H + h) * p.W + w;
       int64_t rpix = pix;
-      if (p.res_shift) rpix = (static_cast<int64_t>(t.n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      if (p.res_shift == 1) rpix = (static_cast<int64_t>(t.n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * 256u +
@@ -975,7 +984,7 @@ tc_conv_rgb_kernel(const TcRgbParams p) {
     const int q = warp & 3;
     const int grp = (warp - 5) >> 2;
     const float alpha = p.alpha ? *p.alpha : 1.f;
-    const EpiArgs ea{p.y, p.bias, nullptr, p.Cout, p.out_bf16, 0, p.act, alpha};
+    const EpiArgs ea{p.y, p.bias, nullptr, p.Cout, p.out_bf16, 0, p.act, alpha, 0};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -1433,7 +1442,9 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   ICGAN_REQUIRE(B > 0 && H > 0 && W > 0, "icgan_conv2d_tc: bad shape B=%d H=%d W=%d", B, H, W);
   ICGAN_REQUIRE(Cin % 16 == 0 && Cin >= 16, "icgan_conv2d_tc: Cin must be a multiple of 16 (got %d)", Cin);
   ICGAN_REQUIRE(Cout % 8 == 0 && Cout >= 8, "icgan_conv2d_tc: Cout must be a multiple of 8 (got %d)", Cout);
-  ICGAN_REQUIRE(!(res_shift && ((H | W) & 1)), "icgan_conv2d_tc: res_shift needs even H, W");
+  ICGAN_REQUIRE(res_shift >= 0 && res_shift <= 2, "icgan_conv2d_tc: res_shift must be 0, 1 or 2 (got %d)", res_shift);
+  ICGAN_REQUIRE(!(res_shift == 1 && ((H | W) & 1)), "icgan_conv2d_tc: res_shift=1 needs even H, W");
+  ICGAN_REQUIRE(!(res_shift == 2 && (!residual || bn_stats)), "icgan_conv2d_tc: res_shift=2 (mask) needs a mask tensor");
 
   if (ksize == 3 && !bn_stats) {
     const int rc = launch_conv_halo(x, wk, alpha_dev, bias, residual, y, B, H, W, Cin, Cout, out_dtype, res_dtype,

@@ -277,11 +277,17 @@ class SNConvFn(torch.autograd.Function):
     using conv1x1(up(x)) == up(conv1x1(x))."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, st: SNState, res_shift: int, act: int, out_dtype, stats=None):
+    def forward(ctx, x, weight, bias, residual, st: SNState, res_shift: int, act: int, out_dtype, stats=None,
+                mask_input: bool = False, act_bwd_in_consumer: bool = False):
+        """mask_input: x is the output of a ReLU whose backward THIS op performs -- the returned input gradient is already
+        gated with (x > 0), inside the dgrad kernel's epilogue on the tensor-core path (the producer passes gradients
+        through: ReluPassFn, or a conv with act_bwd_in_consumer). act_bwd_in_consumer: this op's fused ReLU is
+        differentiated by its (single) consumer, so the incoming gradient is used as is."""
         x = x.contiguous()
         keep = {}
         y = _conv_forward(x, st, bias, residual, res_shift, act, out_dtype, keep=keep, stats=stats)
         ctx.st, ctx.res_shift, ctx.act = st, res_shift, act
+        ctx.mask_input, ctx.act_bwd_in_consumer = mask_input, act_bwd_in_consumer
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.res_dtype = residual.dtype if residual is not None else None
         ctx.save_for_backward(x, y if act != L.ACT_NONE else None, keep.get("xcol"))
@@ -296,7 +302,7 @@ class SNConvFn(torch.autograd.Function):
         cin = x.shape[3]
         k = st.module.weight.shape[2]
         n = dy.numel()
-        if ctx.act == L.ACT_RELU:
+        if ctx.act == L.ACT_RELU and not ctx.act_bwd_in_consumer:
             g = torch.empty_like(dy)
             call("icgan_relu_bwd", ptr(dy), ptr(y), ptr(g), n, dt(y), dt(g), stream_ptr())
             dy = g
@@ -318,7 +324,14 @@ class SNConvFn(torch.autograd.Function):
             call("icgan_channel_sum", ptr(dy), ptr(db), B * H * W, cout, dt(dy), stream_ptr())
         dyc = dy if dy.dtype == x.dtype else dy.to(x.dtype)  # gradients travel in the activation dtype
         if ctx.needs_input_grad[0]:
-            dx = _conv_forward(dyc, st, None, None, 0, L.ACT_NONE, x.dtype, dgrad=True)
+            if ctx.mask_input and st.mode_d == "tc":
+                dx = _conv_forward(dyc, st, None, x, 2, L.ACT_NONE, x.dtype, dgrad=True)  # ReLU gate in the epilogue
+            else:
+                dx = _conv_forward(dyc, st, None, None, 0, L.ACT_NONE, x.dtype, dgrad=True)
+                if ctx.mask_input:
+                    g = torch.empty_like(dx)
+                    call("icgan_relu_bwd", ptr(dx), ptr(x), ptr(g), dx.numel(), dt(x), dt(g), stream_ptr())
+                    dx = g
         if ctx.needs_input_grad[1]:
             if st.mode == "tc":
                 G = torch.zeros(cout, k, k, cin, device=dy.device, dtype=torch.float32)
@@ -342,7 +355,7 @@ class SNConvFn(torch.autograd.Function):
                     call("icgan_conv2d_wgrad_simt", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, 1, k // 2, dt(x),
                          stream_ptr())
             dW = st.weight_grad(G)
-        return dx, dW, db, dres, None, None, None, None, None
+        return dx, dW, db, dres, None, None, None, None, None, None, None
 
 
 # ===================================================================================== linear / embedding
@@ -494,6 +507,21 @@ class ReluFn(torch.autograd.Function):
         dx = torch.empty_like(dy)
         call("icgan_relu_bwd", ptr(dy), ptr(y), ptr(dx), dy.numel(), dt(y), dt(dy), stream_ptr())
         return dx
+
+
+class ReluPassFn(torch.autograd.Function):
+    """relu(x) whose backward is the identity: its consumer (SNConvFn with mask_input=True) applies the gate."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("icgan_relu", ptr(x), ptr(y), x.numel(), dt(x), stream_ptr())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy
 
 
 class Pool2Fn(torch.autograd.Function):

@@ -41,7 +41,9 @@ int icgan_version(void);
  *   y[n,h,w,co] = act( sum_{kh,kw,ci} x[n,h+kh-p,w+kw-p,ci] * wk[co,kh,kw,ci] + bias[co] + residual[...] )
  * x: [B,H,W,Cin] bf16, wk: [Cout,k,k,Cin] bf16, k in {1,3}, stride 1, pad k/2, Cin%16==0, Cout%8==0, H,W powers of two.
  * out_dtype/res_dtype: ICGAN_F32|ICGAN_BF16. residual may be NULL; res_shift=1 reads residual[n,h/2,w/2,co] from a
- * half-resolution tensor (the nearest-upsampled shortcut of GBlock, layers.py:545-552). bias may be NULL.
+ * half-resolution tensor (the nearest-upsampled shortcut of GBlock, layers.py:545-552); res_shift=2 uses `residual` as a
+ * gate instead of an addend, y = residual[n,h,w,co] > 0 ? y : 0 -- the backward of the F.relu that produced this conv's
+ * input (layers.py:594,603 DBlock), fused into the dgrad launch. bias may be NULL.
  * alpha_dev (device scalar, may be NULL): the accumulator is scaled by it before bias -- 1/sigma of SN.W_ (layers.py:112).
  * bn_stats (may be NULL; needs act none, Cout%32==0): float32 [2*Cout], ACCUMULATES sum and sum of squares over all output
  * pixels of (y - bias), i.e. the batch statistics the following ccbn/bn needs (layers.py:412-421), from the fp32
