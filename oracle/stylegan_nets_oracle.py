@@ -266,3 +266,71 @@ def synth_state_dict(shapes: Dict[str, tuple], seed: int) -> SD:
             v = 0.1 * v
         out[k] = torch.from_numpy(np.ascontiguousarray(v))
     return out
+
+
+# ------------------------------------------------------------------------------------------------- loss phases (a23)
+def run_G(g_sd: SD, cfg: StyleGANConfig, z: Tensor, c, h, style_mixing_prob: float, buffers_out: dict):
+    """StyleGAN2Loss.run_G loss.py:57-76: training-mode mapping (w_avg tracked on the first call only), optional style
+    mixing (the same three RNG calls in the same order), synthesis with its default noise_mode='random'."""
+    kw = dict(z_dim=cfg.z_dim, num_layers=cfg.map_layers, num_ws=cfg.num_ws)
+    ws = mapping(g_sd, "mapping", cfg, z, c, h, training=True, w_avg_beta=cfg.w_avg_beta, buffers_out=buffers_out, **kw)
+    if style_mixing_prob > 0:
+        cutoff = torch.empty([], dtype=torch.int64).random_(1, ws.shape[1])
+        cutoff = torch.where(torch.rand([]) < style_mixing_prob, cutoff, torch.full_like(cutoff, ws.shape[1]))
+        ws2 = mapping(g_sd, "mapping", cfg, torch.randn_like(z), c, h, **kw)  # skip_w_avg_update=True
+        ws = torch.cat([ws[:, :int(cutoff)], ws2[:, int(cutoff):]], 1)
+    img = synthesis(g_sd, "synthesis", cfg, ws, noise_mode="random")
+    return img, ws
+
+
+def accumulate_gradients(phase: str, g_sd: SD, d_sd: SD, cfg: StyleGANConfig, real_img, real_c, real_h, gen_z, gen_c,
+                         gen_h, gain: float, *, pl_mean: Tensor, style_mixing_prob: float = 0.9, r1_gamma: float = 10.0,
+                         pl_batch_shrink: int = 2, pl_decay: float = 0.01, pl_weight: float = 2.0) -> dict:
+    """StyleGAN2Loss.accumulate_gradients loss.py:85-194 (no augment pipe).  Gradients accumulate into the `.grad` of
+    whichever state-dict tensors have requires_grad (the caller toggles G / D as training_loop.py:395-425 does).
+    Returns the scalar losses, the updated `pl_mean` and buffer updates (`mapping.w_avg`)."""
+    assert phase in ["Gmain", "Greg", "Gboth", "Dmain", "Dreg", "Dboth"]
+    do_Gmain, do_Dmain = phase in ["Gmain", "Gboth"], phase in ["Dmain", "Dboth"]
+    do_Gpl = phase in ["Greg", "Gboth"] and pl_weight != 0
+    do_Dr1 = phase in ["Dreg", "Dboth"] and r1_gamma != 0
+    out = {"buffers": {}, "pl_mean": pl_mean}
+    sp = torch.nn.functional.softplus
+    if do_Gmain:  # :97-111
+        img, _ = run_G(g_sd, cfg, gen_z, gen_c, gen_h, style_mixing_prob, out["buffers"])
+        loss = sp(-discriminator(d_sd, cfg, img, gen_c, gen_h))
+        out["loss_Gmain"] = loss.detach()
+        loss.mean().mul(gain).backward()
+    if do_Gpl:  # :113-143: path-length regulariser, a double backward through synthesis w.r.t. ws
+        bs = gen_z.shape[0] // pl_batch_shrink
+        img, ws = run_G(g_sd, cfg, gen_z[:bs], None if gen_c is None else gen_c[:bs], None if gen_h is None else gen_h[:bs],
+                        style_mixing_prob, out["buffers"])
+        pl_noise = torch.randn_like(img) / math.sqrt(img.shape[2] * img.shape[3])
+        pl_grads = torch.autograd.grad([(img * pl_noise).sum()], [ws], create_graph=True, only_inputs=True)[0]
+        pl_lengths = pl_grads.square().sum(2).mean(1).sqrt()
+        new_mean = pl_mean.lerp(pl_lengths.mean(), pl_decay)
+        out["pl_mean"] = new_mean.detach()
+        pl_penalty = (pl_lengths - new_mean).square()
+        loss_pl = pl_penalty * pl_weight
+        out["loss_Gpl"] = loss_pl.detach()
+        (img[:, 0, 0, 0] * 0 + loss_pl).mean().mul(gain).backward()
+    loss_dgen = 0
+    if do_Dmain:  # :146-160
+        img, _ = run_G(g_sd, cfg, gen_z, gen_c, gen_h, style_mixing_prob, out["buffers"])
+        loss_dgen = sp(discriminator(d_sd, cfg, img, gen_c, gen_h))
+        out["loss_Dgen"] = loss_dgen.detach()
+        loss_dgen.mean().mul(gain).backward()
+    if do_Dmain or do_Dr1:  # :164-194
+        real_tmp = real_img.detach().requires_grad_(do_Dr1)
+        real_logits = discriminator(d_sd, cfg, real_tmp, real_c, real_h)
+        loss_real = 0
+        if do_Dmain:
+            loss_real = sp(-real_logits)
+            out["loss_Dreal"] = loss_real.detach()
+        loss_r1 = 0
+        if do_Dr1:
+            r1_grads = torch.autograd.grad([real_logits.sum()], [real_tmp], create_graph=True, only_inputs=True)[0]
+            r1_penalty = r1_grads.square().sum([1, 2, 3])
+            loss_r1 = r1_penalty * (r1_gamma / 2)
+            out["loss_Dr1"] = loss_r1.detach()
+        (real_logits * 0 + loss_real + loss_r1).mean().mul(gain).backward()
+    return out

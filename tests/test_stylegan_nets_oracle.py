@@ -108,3 +108,37 @@ def test_minibatch_std_groups():
     for n in range(8):
         assert torch.all(extra[n] == extra[n, 0, 0])
     assert torch.equal(extra[0], extra[2]) and torch.equal(extra[1], extra[3]) and not torch.equal(extra[0], extra[1])
+
+
+@pytest.mark.parametrize("phase,seed,gain", [("Gmain", 31, 1.0), ("Greg", 32, 4.0), ("Dmain", 33, 1.0), ("Dreg", 34, 16.0)])
+def test_loss_phases_match_reference(gold, phase, seed, gain):
+    """StyleGAN2Loss.accumulate_gradients (training/loss.py:85-194) phase by phase: style mixing, random noise, the
+    path-length regulariser (double backward through synthesis) and R1 (double backward through D), against golden
+    gradients from the live reference with the same torch seed."""
+    cfg, meta, _, _, _ = gold
+    fx = dict(np.load(os.path.join(GOLD, "stylegan_loss.npz")))
+    g_sd = O.synth_state_dict(meta["g_shapes"], meta["g_seed"])
+    d_sd = O.synth_state_dict(meta["d_shapes"], meta["d_seed"])
+    g_sd["mapping.w_avg"] = torch.from_numpy(fx[f"{phase}/w_avg_before"])
+    pl_before = {"Gmain": "pl_mean_before", "Greg": "pl_mean_before"}.get(phase)
+    pl_mean = torch.tensor(float(fx[pl_before][0] if pl_before else fx["Greg/pl_mean_after"][0]))
+    is_g = phase.startswith("G")
+    for k, v in (g_sd if is_g else d_sd).items():
+        if v.dtype.is_floating_point and not k.endswith(("resample_filter", "noise_const", "w_avg")):
+            v.requires_grad_(True)
+    z, h, x = inputs()
+    torch.manual_seed(seed)
+    out = O.accumulate_gradients(phase, g_sd, d_sd, cfg, x, None, h, z, None, h, gain, pl_mean=pl_mean)
+    keys = meta["grad_keys_g"] if is_g else meta["grad_keys_d"]
+    sd = g_sd if is_g else d_sd
+    for k in keys:
+        ref = fx[f"{phase}/grad/{k}"]
+        got = sd[k].grad.numpy() if sd[k].grad is not None else np.zeros_like(ref)
+        denom = max(np.linalg.norm(ref), 1e-30)
+        rel = np.linalg.norm(got - ref) / denom
+        assert rel <= 2e-3, f"{phase} grad {k}: rel-L2 {rel:.3e} (|ref| {denom:.3e})"
+    _close(out["pl_mean"].reshape(1), fx[f"{phase}/pl_mean_after"], "pl_mean", tol=1e-5)
+    if "mapping.w_avg" in out["buffers"]:
+        _close(out["buffers"]["mapping.w_avg"], fx[f"{phase}/w_avg_after"], "w_avg", tol=1e-5)
+    else:
+        assert np.array_equal(fx[f"{phase}/w_avg_after"], fx[f"{phase}/w_avg_before"])
