@@ -1,17 +1,21 @@
 // Tensor-core convolution kernels for sm_100a: TMA-staged NHWC tiles -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).
+// All kernels are persistent (one CTA per SM) and warp-specialised: one warp issues TMA, one issues the UMMAs and owns
+// TMEM (both from warp-uniform code under elect.sync), the rest run the epilogue; two TMEM accumulator buffers let the
+// epilogue of tile i overlap the main loop of tile i+1.
 //
-//   tc_conv_kernel  : implicit GEMM  D[pixel, co] = sum_{tap, ci} X[pixel + tap, ci] * Wk[co, tap, ci]
-//                     Forward conv (layers.SNConv2d.forward, BigGAN_PyTorch/layers.py:144-153), its dgrad (same
-//                     kernel, flipped/transposed weight copy), and plain GEMMs (H=1: W plays "rows").
-//                     A tile = 128 output pixels (TW x TH x TN box of the NHWC tensor, one 4-D TMA load per filter
-//                     tap with shifted coordinates; TMA zero-fills the halo => padding costs nothing),
-//                     B tile = BN output channels x cw input channels of one tap. Persistent CTAs, one per SM:
-//                     warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue
-//                     (TMEM -> registers -> bias/residual/activation -> NHWC global). Two TMEM accumulator buffers
-//                     let the epilogue of tile i overlap the main loop of tile i+1.
-//   tc_wgrad_kernel : dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci]   (MN-major UMMA operands read
-//                     directly from the NHWC tensors), all 9 tap accumulators resident in TMEM, split-K over pixel
-//                     ranges with float atomics into the fp32 gradient.
+//   tc_conv_halo_kernel  : 3x3 / pad 1 forward and dgrad for H, W multiples of 16 (layers.SNConv2d.forward,
+//                          BigGAN_PyTorch/layers.py:144-153; dgrad = same kernel on the flipped/transposed weight copy).
+//                          16 x 16-pixel tiles, one 18-row TMA box per horizontal tap offset, the three vertical taps are
+//                          row offsets into it (see the comment at the kernel).
+//   tc_conv_kernel<4|8>  : implicit GEMM with one 128-pixel TMA box per filter tap: 1x1 convs, 3x3 at 4x4 / 8x8, plain
+//                          GEMMs (H = 1); <4> carries the optional batch-norm statistics epilogue.
+//   tc_conv_rgb_kernel   : first conv of D (3 -> ch): im2col built in shared memory by four builder warps.
+//   tc_wgrad_kernel      : dWk[co, tap, ci] += sum_pixels dY[pixel, co] * X[pixel + tap, ci], MN-major UMMA operands read
+//                          straight from the NHWC tensors, taps as column groups, split-K with float atomics.
+//   tc_wgrad_halo_kernel : the same for layers with >= 192 channels: one dx per CTA, the three dy taps are one X box viewed
+//                          at row offsets (N = 192 UMMAs), up to 256 output channels per CTA.
+// Shared epilogue (epilogue_block): y = act(alpha * acc + bias [+ residual | gated by residual > 0]), all global loads
+// of a 32-column block issued before the TMEM load is waited for, 32-byte stores.
 #include <cuda.h>
 #include <stdlib.h>
 
