@@ -36,6 +36,12 @@ WORKLOADS = {
                  class_cond=False, G_f=14.52, D_f=2.23, per_gpu_batch=256, micro_batch=128),
 }
 METRIC = "images/sec G+D step, IC-GAN BigGAN"
+JSON_OUT = [None]  # where the one JSON line goes (the original stdout when fd 1 has been pointed at stderr)
+
+
+def emit(line):
+    out = JSON_OUT[0] or sys.stdout
+    print(json.dumps(line), file=out, flush=True)
 
 
 def model_kwargs(w):
@@ -139,16 +145,26 @@ def oracle_pool_rate(workload, batch, steps, warmup):
     reference's data parallelism would place them), each timing `steps` oracle train_steps at micro-batch `batch`.
     Returns (aggregate images/s, mean seconds per step, workers, threads per worker)."""
     import subprocess
-    cores = os.cpu_count() or 1
+    # the cores this process may actually run on (cgroup cpusets make cpu_count() lie), each worker pinned to its own
+    # disjoint set so that two hosts with the same core count time the same thing (round 1: 5x host-to-host spread)
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = list(range(os.cpu_count() or 1))
+    cores = len(avail)
     threads = min(ORACLE_THREADS, cores)
     workers = max(1, cores // threads)
-    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="",
+               OMP_PROC_BIND="close", OMP_PLACES="cores")
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         env.pop(k, None)
     cmd = [sys.executable, os.path.abspath(__file__), "--oracle-worker", "--workload", workload, "--steps", str(steps),
            "--warmup", str(warmup), "--cpu-batch", str(batch), "--threads", str(threads)]
-    procs = [subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-             for _ in range(workers)]
+    procs = []
+    for i in range(workers):
+        mine = avail[i * threads:(i + 1) * threads]
+        procs.append(subprocess.Popen(cmd + ["--affinity", ",".join(map(str, mine))], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
     dts = []
     for pr in procs:
         out, err = pr.communicate()
@@ -159,6 +175,11 @@ def oracle_pool_rate(workload, batch, steps, warmup):
 
 
 def run_oracle_worker(args, w):
+    if args.affinity:
+        try:
+            os.sched_setaffinity(0, {int(c) for c in args.affinity.split(",")})
+        except (AttributeError, OSError):
+            pass
     ips, dt = oracle_step_rate(w, args.cpu_batch, args.steps, args.warmup, args.threads)
     print(json.dumps({"dt": dt, "ips": ips}), flush=True)
 
@@ -179,7 +200,184 @@ def run_reference(args, w):
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+# ------------------------------------------------------------------------------------------------- kNN build (config 5)
+KNN_D, KNN_K = 2048, 50
+
+
+def knn_cpu_rate(n_sample):
+    """queries/s of the oracle (exact float64 restatement of _obtain_nns: BLAS X.X^T blocks + argpartition + exact re-rank)
+    on an n_sample-row database with all host threads; the caller extrapolates to N by the N^2 work law."""
+    import numpy as np
+    from oracle import knn_oracle as K
+    rng = np.random.default_rng(6)
+    x = K.normalize_features(rng.standard_normal((n_sample, KNN_D)))
+    t0 = time.perf_counter()
+    K.obtain_nns(x, KNN_K)
+    return n_sample / (time.perf_counter() - t0)
+
+
+def run_knn(args):
+    """BASELINE config 5: brute-force k-NN build over N x 2048 float32 instance features, k = 50.  A "step" is one complete
+    build of this rank's query-row shard (split-bf16 tensor-core distance sweep with fused top-64 selection, exact float64
+    re-rank + certification, device fallback for uncertified rows); database replicated, query rows sharded, one
+    all_gather of the results at the end.  value = queries/s of the whole job."""
+    import numpy as np
+    import torch.distributed as dist
+    from ic_gan_b200 import _lib, knn
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    N = args.knn_n
+    if args.impl == "reference":
+        if rank:
+            return
+        ns = min(N, 16384)
+        qps = knn_cpu_rate(ns)
+        full = qps * ns / N
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        sample = (f"oracle obtain_nns (float64 BLAS X.X^T blocks + argpartition + exact re-rank) on a {ns}-row database, "
+                  f"{qps:.1f} queries/s there, extrapolated x {ns}/{N} (work per query is proportional to N)")
+        emit({"impl": "reference", "metric": f"queries/sec kNN build (N={N}, d={KNN_D}, k={KNN_K})", "value": full,
+              "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": N / full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "f64", "data": "synthetic", "config": {"workload": f"kNN build N={N}", "host_threads": cores},
+              "cpu_baseline": {"value": full, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+              "e2e": {"value": full, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+              "gpu_launches": 0})
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("ICGAN_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        sys.stdout.flush()
+        JSON_OUT[0] = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    gen = torch.Generator(device=dev).manual_seed(6)  # same table on every rank (replicated database)
+    X = torch.empty(N, KNN_D, device=dev, dtype=torch.float32)
+    for c0 in range(0, N, 65536):  # randn -> float64 normalise -> float32 (datasets_common.py:422-428), chunked
+        blk = torch.randn(min(65536, N - c0), KNN_D, device=dev, generator=gen, dtype=torch.float64)
+        X[c0:c0 + blk.shape[0]] = (blk / blk.norm(dim=1, keepdim=True)).float()
+    q0, q1 = rank * N // world, (rank + 1) * N // world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    coarse_ev = []
+
+    def build(rows, gather=True):
+        res = knn.obtain_nns(X, KNN_K, rows=rows, timing=coarse_ev)
+        if world > 1 and gather:  # [N/W, 50] int64 + [N/W] float64 per rank, padded to the largest shard
+            m = (N + world - 1) // world
+            nn_pad = torch.full((m, KNN_K), -1, device=dev, dtype=torch.int64)
+            rd_pad = torch.zeros(m, device=dev, dtype=torch.float64)
+            nn_pad[:rows[1] - rows[0]] = res.sample_nns
+            rd_pad[:rows[1] - rows[0]] = res.sample_nns_radius
+            all_nn = torch.empty(world * m, KNN_K, device=dev, dtype=torch.int64)
+            all_rd = torch.empty(world * m, device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(all_nn, nn_pad)
+            dist.all_gather_into_tensor(all_rd, rd_pad)
+        return res
+
+    for _ in range(max(1, args.warmup)):  # warm-up on a 1/16 slice of the shard (same kernels, same table)
+        build((q0, q0 + max(256, (q1 - q0) // 16)), gather=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    del coarse_ev[:]
+    launches0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = build((q0, q1))
+    e1.record()
+    barrier()
+    launches = _lib.LAUNCHES - launches0
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    coarse_ms = sum(a.elapsed_time(b) for a, b in coarse_ev) / args.steps
+    # spot check inside the bench: rows of this shard against a float64 brute force on the device
+    rows = torch.randint(q0, q1, (16,), generator=torch.Generator().manual_seed(rank)).tolist()
+    bad = 0
+    for r in rows:
+        d2 = torch.empty(N, device=dev, dtype=torch.float64)
+        for c0 in range(0, N, 131072):
+            diff = X[c0:c0 + 131072].double() - X[r].double()[None, :]
+            d2[c0:c0 + 131072] = (diff * diff).sum(1)
+        m = KNN_K + 17
+        vals, idx = torch.topk(d2, m, largest=False)
+        order = np.lexsort((idx.cpu().numpy(), vals.cpu().numpy()))
+        cand = idx.cpu().numpy()[order][:KNN_K + 1]
+        keep = cand[cand != r][:KNN_K]
+        bad += int(not np.array_equal(keep, res.sample_nns[r - q0].cpu().numpy()))
+    # ---- e2e: host features in (pinned), neighbour tables out to the host
+    e2e = None
+    if not args.no_e2e:
+        Xh = torch.empty(N, KNN_D, dtype=torch.float32).pin_memory()
+        Xh.copy_(X)
+        out_nn = torch.empty(q1 - q0, KNN_K, dtype=torch.int64).pin_memory()
+        out_rd = torch.empty(q1 - q0, dtype=torch.float64).pin_memory()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            X.copy_(Xh, non_blocking=True)
+            r2 = knn.obtain_nns(X, KNN_K, rows=(q0, q1))
+            out_nn.copy_(r2.sample_nns, non_blocking=True)
+            out_rd.copy_(r2.sample_nns_radius, non_blocking=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": N / (float(t.item()) * 1e-3), "unit": "queries/s", "ms_per_step": float(t.item()),
+               "h2d_bytes_per_step": N * KNN_D * 4, "d2h_bytes_per_step": (q1 - q0) * (KNN_K * 8 + 8)}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    nq = q1 - q0
+    alg = 2.0 * nq * N * KNN_D  # SURVEY.md section 8d: 2*N^2*d for the whole job; this rank's share
+    ach = alg / (coarse_ms * 1e-3) * 1e-12
+    line = {"metric": f"queries/sec kNN build (N={N}, d={KNN_D}, k={KNN_K})", "value": N / (ms * 1e-3),
+            "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16x3 (split) + f64 re-rank",
+            "data": "synthetic",
+            "config": {"workload": f"kNN conditioning build, N={N} x {KNN_D} float32, k={KNN_K}, bit-exact indices",
+                       "query_rows_per_gpu": nq, "parallelism": f"query-sharded x{world}, database replicated",
+                       "l2": "inputs larger than L2", "seconds_per_build": ms * 1e-3,
+                       "uncertified_rows": res.stats["uncertified_rows"], "spot_check_rows": len(rows),
+                       "spot_check_mismatches": bad,
+                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
+            "roofline": {"kernel": "knn_coarse_kernel (split-bf16 distance sweep + fused top-64 selection)",
+                         "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tf_sustained"], "traffic": None,
+                         "note": "achieved = ALGORITHMIC 2*nq*N*d / kernel time; the kernel executes 3 bf16 products per "
+                                 f"algorithmic one, i.e. {3 * ach:.0f} TFLOP/s of tensor-pipe work",
+                         "kernel_ms_per_step": coarse_ms, "share_of_step": coarse_ms / ms,
+                         "peak_source": pk["source"] + ", sustained"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        ns = 16384
+        qps = knn_cpu_rate(ns)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        line["cpu_baseline"] = {"value": qps * ns / N, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "sample": f"oracle obtain_nns on a {ns}-row database ({qps:.1f} queries/s), extrapolated "
+                                          f"x {ns}/{N} (work per query proportional to N)"}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------- B200 arm
@@ -189,7 +387,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cc256", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cc256", choices=sorted(WORKLOADS) + ["knn"])
+    ap.add_argument("--knn-n", type=int, default=1281167, help="database rows of --workload knn")
     ap.add_argument("--per-gpu-batch", type=int, default=0)
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
@@ -198,9 +397,12 @@ def main():
     ap.add_argument("--oracle-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-batch", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--threads", type=int, default=ORACLE_THREADS, help=argparse.SUPPRESS)
+    ap.add_argument("--affinity", default="", help=argparse.SUPPRESS)
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: short warm-up allowed, no e2e/cpu legs "
                                                        "(a number printed by such a run is never a bench value)")
     args = ap.parse_args()
+    if args.workload == "knn":
+        return run_knn(args)
     w = dict(WORKLOADS[args.workload])
     if args.per_gpu_batch:
         w["per_gpu_batch"] = args.per_gpu_batch
@@ -220,6 +422,7 @@ def main():
     from ic_gan_b200.biggan import G_D, Discriminator, Generator
     from ic_gan_b200.biggan import train_fns
     from ic_gan_b200.dist import GradSync
+    from ic_gan_b200.optim import FusedAdamEMA
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,7 +433,13 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("ICGAN_NCCL_DEBUG", "WARN")  # stdout carries exactly one JSON line
+        # NCCL's communicator lines ("... nranks N ...") are evidence the driver reads; they go to stderr, stdout carries
+        # exactly one JSON line: fd 1 is pointed at stderr for the whole run and the JSON is written to the saved fd.
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("ICGAN_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        sys.stdout.flush()
+        JSON_OUT[0] = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -247,12 +456,15 @@ def main():
     for net in (G, D):
         net.init = "N02"
         net.init_weights()
-    sync = GradSync({"G": G, "D": D}, world)
+    # Adam + EMA: one kernel launch per network over flat parameter / gradient / moment / EMA buffers (ic_gan_b200/optim.py);
+    # the data-parallel all-reduce runs on the same flat gradient buffers and its 1/world rides in the step kernel
+    opt_G = FusedAdamEMA(G.parameters(), lr=4e-5, betas=(0.0, 0.999), eps=1e-6, ema_params=G_ema.parameters())
+    opt_D = FusedAdamEMA(D.parameters(), lr=1e-4, betas=(0.0, 0.999), eps=1e-6)
+    sync = GradSync({"G": G, "D": D}, world, optimizers={"G": opt_G, "D": opt_D})
     sync.broadcast_params()
-    opt_G = torch.optim.Adam(G.parameters(), lr=4e-5, betas=(0.0, 0.999), weight_decay=0, eps=1e-6, fused=True)
-    opt_D = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.999), weight_decay=0, eps=1e-6, fused=True)
     GD = G_D(G, D, opt_G, opt_D)
     ema = train_fns.ema(G, G_ema, 0.9999, 20000)
+    ema.fuse_into(opt_G)
     state = {"itr": 0}
     config = {"toggle_grads": True, "num_D_steps": 1, "num_D_accumulations": acc, "num_G_accumulations": acc,
               "split_D": False, "ema": True, "D_ortho": 0.0, "G_ortho": 0.0, "DA": False, "DiffAugment": False}
@@ -275,7 +487,7 @@ def main():
         return (z_pool[i], yg_pool[i], fg_pool[i]) if cc else (z_pool[i], fg_pool[i])
 
     train_dev = train_fns.GAN_training_function(G, D, GD, ema, state, config, sample_dev, embedded_optimizers=False,
-                                                device=dev, batch_size=m, grad_sync=sync)
+                                                device=dev, batch_size=m, grad_sync=sync, lazy_losses=True)
 
     def step_dev():
         sync.broadcast_buffers()
@@ -344,7 +556,7 @@ def main():
             yd = y_host.to(dev, non_blocking=True) if cc else None
             out = train_host(xd, yd, fd)
             state["itr"] += 1
-            return float(out["G_loss"].item()) + float(out["D_loss_real"].item()) + float(out["D_loss_fake"].item())
+            return out["G_loss"] + out["D_loss_real"] + out["D_loss_fake"]  # Python floats: train() read them back (12 B)
 
         step_host()
         barrier()
@@ -414,7 +626,7 @@ def main():
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": w["name"], "per_gpu_batch": Bg, "micro_batch": m, "accumulations": acc,
                        "global_batch": Bg * world, "parallelism": f"dp{world}", "l2": "inputs larger than L2",
-                       "optimizer": "torch.optim.Adam(fused) x2 + EMA", "step_gflop_per_image": f_step,
+                       "optimizer": "icgan_adam_ema_step: Adam + EMA fused, one launch per network", "step_gflop_per_image": f_step,
                        "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
             "roofline": roofline,
             "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},
@@ -426,7 +638,7 @@ def main():
                                 "sample": f"1 warm oracle G+D step (CPU restatement of train_fns.py:40-191) in each of "
                                           f"{workers} worker processes x {threads} threads, micro-batch {cb}, fp32, "
                                           f"{dt:.1f} s per step"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

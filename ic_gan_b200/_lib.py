@@ -21,7 +21,7 @@ ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
 _lib: Optional[C.CDLL] = None
 
-vp, fp, i32, i64, f32 = C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float
+vp, fp, i32, i64, f32, f64 = C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 
 class IcganSnLayer(C.Structure):
@@ -67,6 +67,8 @@ SIGNATURES = {
     "icgan_bias_act": [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, f32, f32, f32, i32, vp],
     "icgan_upfirdn2d": [vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
                         i32, vp],
+    "icgan_adam_ema_step": [fp, fp, fp, fp, fp, i64, f64, f64, f64, f64, i64, f64, f64, vp],
+    "icgan_ema_lerp": [fp, fp, i64, f64, vp],
     "icgan_gemm_tc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
     "icgan_gemm": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, fp, f32, fp, i32,
                    i32, i32, vp],
@@ -131,4 +133,7 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
         return None
     if not t.is_cuda:
         raise RuntimeError("ic_gan_b200 kernels need CUDA tensors (there is no CPU path)")
+    if not (t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))):
+        # the kernels index dense memory; a strided view (or a channels_last-converted OIHW weight) would be read as garbage
+        raise RuntimeError(f"ic_gan_b200 kernels need dense tensors; got shape {tuple(t.shape)} strides {t.stride()}")
     return t.data_ptr()

@@ -36,9 +36,25 @@ class ema(object):
         with torch.no_grad():
             for k in self.source_dict:
                 self.target_dict[k].data.copy_(self.source_dict[k].data)
+        self.fused_optimizer = None  # set by fuse_into(): the parameter half then rides in the optimiser's kernel
+        self.buffer_ema = None
+
+    def decay_at(self, itr=None):
+        return 0.0 if (itr and itr < self.start_itr) else self.decay  # utils.py:1058: itr == 0 uses the real decay
+
+    def fuse_into(self, optimizer):
+        """Let `optimizer` (ic_gan_b200.optim.FusedAdamEMA built with ema_params=target.parameters()) apply the parameter
+        half of the average inside its step kernel; update() then only averages the buffers (one launch)."""
+        from ..optim import FlatBufferEMA
+        self.fused_optimizer = optimizer
+        self.buffer_ema = FlatBufferEMA(self.source, self.target)
+        self.source_dict, self.target_dict = self.source.state_dict(), self.target.state_dict()
 
     def update(self, itr=None):
-        decay = 0.0 if (itr is not None and itr < self.start_itr) else self.decay
+        decay = self.decay_at(itr)
+        if self.fused_optimizer is not None:  # parameters were averaged by the optimiser step that just ran
+            self.buffer_ema.update(decay)
+            return
         with torch.no_grad():
             keys = [k for k in self.source_dict if self.target_dict[k].dtype.is_floating_point]
             tgt = [self.target_dict[k].data for k in keys]
@@ -48,7 +64,10 @@ class ema(object):
 
 
 def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditionings, embedded_optimizers=True,
-                          device="cuda", batch_size=0, grad_sync=None):
+                          device="cuda", batch_size=0, grad_sync=None, lazy_losses=False):
+    """`grad_sync` / `lazy_losses` are extensions (defaults = reference behaviour): see the module docstring; with
+    lazy_losses=True train() returns 0-d device tensors instead of the reference's Python floats (train_fns.py:183-187),
+    leaving the host free to queue the next step."""
     def _opt(net, name):
         return net.optim if embedded_optimizers else getattr(GD, name)
 
@@ -66,11 +85,15 @@ def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditioning
             z_, f_g = cond
         else:
             z_ = cond[0] if isinstance(cond, (tuple, list)) else cond
+        if n is not None:  # the D phase slices the draw to the micro-batch (train_fns.py:82-88); the G phase does not (:144-150)
+            z_ = z_[:n]
+            labels_g = labels_g[:n] if labels_g is not None else None
+            f_g = f_g[:n] if f_g is not None else None
         if labels_g is not None:
-            labels_g = labels_g[:n].to(device, non_blocking=True).long()
+            labels_g = labels_g.to(device, non_blocking=True).long()
         if f_g is not None:
-            f_g = f_g[:n].to(device, non_blocking=True)
-        return z_[:n].to(device, non_blocking=True), labels_g, f_g
+            f_g = f_g.to(device, non_blocking=True)
+        return z_.to(device, non_blocking=True), labels_g, f_g
 
     def train(x, y=None, features=None):
         opt_G, opt_D = _opt(G, "optimizer_G"), _opt(D, "optimizer_D")
@@ -103,9 +126,8 @@ def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditioning
             toggle_grad(D, False)
             toggle_grad(G, True)
         _zero(opt_G)
-        n_full = x.shape[0] if config.get("G_batch_size", 0) in (0, None) else config["G_batch_size"]
         for _ in range(config["num_G_accumulations"]):
-            z_, labels_g, f_g = _draw(y is not None, features is not None, batch_size if batch_size else n_full)
+            z_, labels_g, f_g = _draw(y is not None, features is not None, None)
             D_fake = GD(z_, labels_g, f_g, train_G=True, split_D=config["split_D"],
                         policy=config.get("DiffAugment", False), DA=config.get("DA", False))
             G_loss = loss_hinge_gen(D_fake) / float(config["num_G_accumulations"])
@@ -114,9 +136,15 @@ def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditioning
             raise NotImplementedError("ortho regularisation is off in every IC-GAN config")
         if grad_sync is not None:
             grad_sync.sync("G")
+        if config["ema"] and getattr(ema, "fused_optimizer", None) is opt_G:
+            opt_G.set_ema_decay(ema.decay_at(state_dict["itr"]))
         opt_G.step()
         if config["ema"]:
             ema.update(state_dict["itr"])
-        return {"G_loss": G_loss.detach(), "D_loss_real": D_loss_real.detach(), "D_loss_fake": D_loss_fake.detach()}
+        out = {"G_loss": G_loss.detach(), "D_loss_real": D_loss_real.detach(), "D_loss_fake": D_loss_fake.detach()}
+        if lazy_losses:
+            return out
+        vals = torch.stack([out["G_loss"].float(), out["D_loss_real"].float(), out["D_loss_fake"].float()]).tolist()
+        return {"G_loss": vals[0], "D_loss_real": vals[1], "D_loss_fake": vals[2]}  # one device->host read (12 bytes)
 
     return train

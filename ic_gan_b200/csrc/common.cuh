@@ -42,6 +42,17 @@ __device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p, int64_t i) 
 __device__ __forceinline__ void st_from_float(float* p, int64_t i, float v) { p[i] = v; }
 __device__ __forceinline__ void st_from_float(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
 
+// cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs must opt every one of them in.  Returns true the
+// first time it is called for the current device with a given (function-local static) mask.
+inline bool first_use_on_this_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -407,10 +407,9 @@ extern "C" int icgan_knn_coarse(const void* Xhi, const void* Xlo, const float* n
   if (!rc) rc = make_map2(&bhi, Xhi, d, N, kKnnBN);
   if (!rc) rc = make_map2(&blo, Xlo, d, N, kKnnBN);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
     ICGAN_CUDA(cudaFuncSetAttribute(knn_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmem));
-    configured = true;
   }
   const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail + 1024u;
   const int grid = p.row_tiles < num_sms() ? p.row_tiles : num_sms();

@@ -793,10 +793,9 @@ static int launch_conv_halo(const void* x, const void* wk, const float* alpha_de
     if (rc) return rc;
   }
   const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
     ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   tc_conv_halo_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmA, tmB, p);
@@ -1404,10 +1403,9 @@ static int launch_wgrad_halo(const void* x, const void* dy, float* dwk, int B, i
     if (rc) return rc;
   }
   const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
     ICGAN_CUDA(cudaFuncSetAttribute(tc_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = true;
   }
   const int grid = out_tiles * p.splits;
   tc_wgrad_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmDy, tmX, p);
@@ -1519,11 +1517,10 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
     if (rc) return rc;
   }
   const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
     ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (bn_stats) tc_conv_kernel<4><<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
@@ -1553,11 +1550,10 @@ extern "C" int icgan_conv2d_rgb_tc(const void* x, const void* wcol, const float*
   p.y = y; p.bias = bias; p.alpha = alpha_dev;
   const uint32_t smem_bytes = 1024u + kRgbBufs * 8192u + 256u * 64u + 512u;
   ICGAN_REQUIRE(Cs <= 3, "icgan_conv2d_rgb_tc: at most 3 input channels (got %d)", Cs);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
     ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_rgb_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_rgb_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (ksize == 3 && Cs == 3)
@@ -1632,10 +1628,9 @@ extern "C" int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, 
     if (rc) return rc;
   }
   const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
     ICGAN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = true;
   }
   const int grid = out_tiles * p.splits;
   tc_wgrad_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmDy, tmX, p);

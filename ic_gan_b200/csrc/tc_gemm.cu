@@ -312,10 +312,9 @@ extern "C" int icgan_gemm_tc(const void* A, const void* B, void* C, int M, int N
   else rc = make_map3(&tmB, B, N, K, batch, ldb, sbb, 64, kKC);
   if (rc) return rc;
   const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
     ICGAN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudgetG));
-    configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   tc_gemm_kernel<<<grid, kThreadsG, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);

@@ -30,12 +30,24 @@ class FlatGrads:
         self.flat.zero_()
 
 
+class _Existing:
+    def __init__(self, flat: torch.Tensor):
+        self.flat = flat
+
+    def zero(self):
+        self.flat.zero_()
+
+
 class GradSync:
     """grad_sync object for GAN_training_function: sync("D") / sync("G") -> one all-reduce (mean) each."""
 
-    def __init__(self, nets: Dict[str, torch.nn.Module], world_size: int):
+    def __init__(self, nets: Dict[str, torch.nn.Module], world_size: int, optimizers: Dict[str, object] = None):
+        """optimizers[k] may be an ic_gan_b200.optim.FusedAdamEMA: its flat gradient buffer is the one all-reduced and the
+        1/world of the mean is folded into its step kernel (no separate scaling pass over the buffer)."""
         self.world = world_size
-        self.flat = {k: FlatGrads(net.parameters()) for k, net in nets.items()}
+        self.opt = {k: (optimizers or {}).get(k) for k in nets}
+        self.flat = {k: (_Existing(self.opt[k].flat_g) if hasattr(self.opt[k], "flat_g") else FlatGrads(net.parameters()))
+                     for k, net in nets.items()}
         self.nets = nets
         self.calls = 0
 
@@ -43,7 +55,10 @@ class GradSync:
         if self.world > 1:
             buf = self.flat[which].flat
             dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-            buf.mul_(1.0 / self.world)
+            if hasattr(self.opt[which], "set_grad_scale"):
+                self.opt[which].set_grad_scale(1.0 / self.world)
+            else:
+                buf.mul_(1.0 / self.world)
             self.calls += 1
 
     def broadcast_buffers(self):

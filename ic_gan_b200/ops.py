@@ -83,13 +83,8 @@ class SNState:
             return
         self.key, self.version = key, None
         self.rows, self.cols = rows, cols
-        self.aux = torch.zeros(cols + rows + 4, device=w.device, dtype=torch.float32)
-        self.v = self.aux[:cols]
-        self.u_new = self.aux[cols:cols + rows]
-        self.sigma = self.aux[cols + rows:cols + rows + 2]
-        self.scratch = self.aux[cols + rows + 2:]
+        self.bind_aux(torch.zeros(cols + rows + 4, device=w.device, dtype=torch.float32))
         self.sigma.fill_(1.0)
-        self.alpha = self.sigma[1:] if self.use_sn else None  # device scalar 1/sigma
         self.wk_fwd = self.wk_dgrad = self.wk_fwd32 = self.wk_dgrad32 = None
         self.mode = self.mode_d = "plain"
         if self.kind != "conv":
@@ -112,6 +107,24 @@ class SNState:
         self.mode, self.mode_d = pick(ci, co), pick(co, ci)
         self.kp = (k * k * ci + 15) // 16 * 16   # im2col width of the forward / of the dgrad ("col" modes)
         self.kp_d = (k * k * co + 15) // 16 * 16
+
+    def bind_aux(self, aux: Tensor):
+        """aux = v[cols] | u'[rows] | sigma, 1/sigma | scratch[2]: the LIVE spectral-norm state the power iteration writes."""
+        rows, cols = self.rows, self.cols
+        self.aux = aux
+        self.v = aux[:cols]
+        self.u_new = aux[cols:cols + rows]
+        self.sigma = aux[cols + rows:cols + rows + 2]
+        self.scratch = aux[cols + rows + 2:cols + rows + 4]
+        self.alpha = self.sigma[1:] if self.use_sn else None  # device scalar 1/sigma
+        self.bind_snapshot(aux)
+
+    def bind_snapshot(self, snap: Tensor):
+        """Per-forward copy of (v, u', sigma, 1/sigma): what THIS forward's graph is differentiated with.  The live buffers
+        are overwritten by the next forward (G_D with split_D=True runs D twice before one backward; the reference keeps
+        sigma in each graph, layers.py:98-112)."""
+        rows, cols = self.rows, self.cols
+        self.snap = (snap[:cols], snap[cols:cols + rows], snap[cols + rows:cols + rows + 2])
 
     def descriptor(self) -> L.IcganSnLayer:
         m = self.module
@@ -155,8 +168,10 @@ class SNState:
         self.wk_fwd = self._operand(f32, self.mode, self.kp)
         self.wk_dgrad = self._operand(d32, self.mode_d, self.kp_d)
 
-    def weight_grad(self, G: Tensor) -> Tensor:
-        """dL/dW (master layout) from G = dL/d(W/sigma) given in operand layout (float32)."""
+    def weight_grad(self, G: Tensor, snap=None) -> Tensor:
+        """dL/dW (master layout) from G = dL/d(W/sigma) given in operand layout (float32); `snap` = the (v, u', sigma)
+        snapshot of the forward being differentiated."""
+        v, u_new, sigma = snap if snap is not None else (self.v, self.u_new, self.sigma)
         w = self.module.weight
         dW = torch.empty_like(w)
         if self.kind == "conv":
@@ -164,7 +179,7 @@ class SNState:
         else:
             co, ci, k = self.rows, self.cols, 1
         if self.use_sn:
-            call("icgan_sn_weight_grad", ptr(G), ptr(w), ptr(self.u_new), ptr(self.v), ptr(self.sigma),
+            call("icgan_sn_weight_grad", ptr(G), ptr(w), ptr(u_new), ptr(v), ptr(sigma),
                  ptr(self.scratch), ptr(dW), co, ci, k, stream_ptr())
         else:
             call("icgan_sn_weight_grad", ptr(G), None, None, None, None, None, ptr(dW), co, ci, k, stream_ptr())
@@ -182,6 +197,13 @@ def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype,
     if sn_states:
         key = tuple(s.key for s in sn_states)
         if table_cache.get("key") != key:
+            # all layers' (v, u', sigma, scratch) live in ONE flat buffer so that a forward can snapshot them in one copy
+            sizes = [s.cols + s.rows + 4 for s in sn_states]
+            flat = torch.zeros(sum(sizes), device=sn_states[0].module.weight.device, dtype=torch.float32)
+            for s, view in zip(sn_states, flat.split(sizes)):
+                s.bind_aux(view)
+                s.sigma.fill_(1.0)
+            table_cache["flat"], table_cache["sizes"] = flat, sizes
             arr = (L.IcganSnLayer * len(sn_states))(*[s.descriptor() for s in sn_states])
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             table_cache["table"] = host.to(sn_states[0].module.weight.device)
@@ -194,6 +216,9 @@ def refresh_sn(states: List[SNState], training: bool, eps: float, compute_dtype,
         if training:  # sv0 is a log-only buffer (layers.py:108-111)
             with torch.no_grad():
                 torch._foreach_copy_([s.module.sv0 for s in sn_states], [s.sigma[:1] for s in sn_states])
+        snap = table_cache["flat"].clone()
+        for s, view in zip(sn_states, snap.split(table_cache["sizes"])):
+            s.bind_snapshot(view)
     for s in states:
         s.prepare()
         s.fresh = True
@@ -216,9 +241,11 @@ def _im2col(x: Tensor, k: int, kp: int) -> Tensor:
 
 
 def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: int, out_dtype, dgrad: bool = False,
-                  keep: Optional[dict] = None, stats: Optional[Tensor] = None):
-    """act(alpha * conv(x, operand) + bias + residual); `keep` receives tensors worth saving for the backward."""
+                  keep: Optional[dict] = None, stats: Optional[Tensor] = None, snap=None):
+    """act(alpha * conv(x, operand) + bias + residual); `keep` receives tensors worth saving for the backward.
+    `snap`: (v, u', sigma) snapshot whose 1/sigma is used instead of the live one (backward of an earlier forward)."""
     B, H, W, cin = x.shape
+    alpha = st.alpha if (snap is None or not st.use_sn) else snap[2][1:]
     wk, mode, kp = (st.wk_fwd, st.mode, st.kp) if not dgrad else (st.wk_dgrad, st.mode_d, st.kp_d)
     w = st.module.weight
     cout, k = (w.shape[0], w.shape[2]) if not dgrad else (w.shape[1], w.shape[2])
@@ -226,14 +253,14 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
         raise RuntimeError("fused batch-norm statistics need the tensor-core conv path")
     if mode == "tc":
         y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
-        _tc_conv(x, wk, st.alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act, stats)
+        _tc_conv(x, wk, alpha, bias, residual, y, B, H, W, cin, cout, k, res_shift, act, stats)
         return y
     if mode == "col" and kp == 32 and cin <= 3 and cout <= 256 and residual is None and x.dtype == torch.bfloat16:
         # RGB-side input, im2col fused into the kernel; the backward rebuilds the column buffer only if it needs it
         y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
         _SHAPE[0] = (B, H, W, cin, cout, k)
         _timed("tc_conv_kernel", 2.0 * B * H * W * cout * cin * k * k,
-               lambda: call("icgan_conv2d_rgb_tc", ptr(x), ptr(wk), ptr(st.alpha), ptr(bias), ptr(y), B, H, W, cin, cout, k,
+               lambda: call("icgan_conv2d_rgb_tc", ptr(x), ptr(wk), ptr(alpha), ptr(bias), ptr(y), B, H, W, cin, cout, k,
                             dt(y), act, stream_ptr()))
         return y
     if mode == "col":  # RGB-side input: im2col (27 -> 32 columns) + tensor-core 1x1
@@ -241,7 +268,7 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
         if keep is not None:
             keep["xcol"] = xcol
         y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
-        _tc_conv(xcol, wk, st.alpha, bias, residual, y, B, H, W, kp, cout, 1, res_shift, act)
+        _tc_conv(xcol, wk, alpha, bias, residual, y, B, H, W, kp, cout, 1, res_shift, act)
         return y
     if mode == "pad8":  # RGB-side output: 8 padded output channels, first `cout` kept
         if residual is not None:
@@ -251,16 +278,16 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
             b8 = torch.zeros(8, device=x.device, dtype=torch.float32)
             b8[:cout] = bias
         y8 = torch.empty(B, H, W, 8, device=x.device, dtype=out_dtype)
-        _tc_conv(x, wk, st.alpha, b8, None, y8, B, H, W, cin, 8, k, 0, act)
+        _tc_conv(x, wk, alpha, b8, None, y8, B, H, W, cin, 8, k, 0, act)
         return y8[..., :cout].contiguous()
     # float32 CUDA-core kernels
     y = torch.empty(B, H, W, cout, device=x.device, dtype=out_dtype)
     if min(cin, cout) <= 4 and residual is None:
-        call("icgan_conv2d_small", ptr(x), ptr(wk), ptr(st.alpha), ptr(bias), ptr(y), B, H, W, cin, cout, k, dt(x), dt(y),
+        call("icgan_conv2d_small", ptr(x), ptr(wk), ptr(alpha), ptr(bias), ptr(y), B, H, W, cin, cout, k, dt(x), dt(y),
              act, stream_ptr())
     else:
         rdt = dt(residual) if residual is not None else L.F32
-        call("icgan_conv2d_simt", ptr(x), ptr(wk), ptr(st.alpha), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k,
+        call("icgan_conv2d_simt", ptr(x), ptr(wk), ptr(alpha), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, k,
              1, k // 2, dt(x), dt(y), rdt, res_shift, act, stream_ptr())
     return y
 
@@ -287,6 +314,7 @@ class SNConvFn(torch.autograd.Function):
         keep = {}
         y = _conv_forward(x, st, bias, residual, res_shift, act, out_dtype, keep=keep, stats=stats)
         ctx.st, ctx.res_shift, ctx.act = st, res_shift, act
+        ctx.snap = st.snap  # this forward's (v, u', sigma): the live buffers may be overwritten before the backward runs
         ctx.mask_input, ctx.act_bwd_in_consumer = mask_input, act_bwd_in_consumer
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.res_dtype = residual.dtype if residual is not None else None
@@ -325,9 +353,9 @@ class SNConvFn(torch.autograd.Function):
         dyc = dy if dy.dtype == x.dtype else dy.to(x.dtype)  # gradients travel in the activation dtype
         if ctx.needs_input_grad[0]:
             if ctx.mask_input and st.mode_d == "tc":
-                dx = _conv_forward(dyc, st, None, x, 2, L.ACT_NONE, x.dtype, dgrad=True)  # ReLU gate in the epilogue
+                dx = _conv_forward(dyc, st, None, x, 2, L.ACT_NONE, x.dtype, dgrad=True, snap=ctx.snap)  # ReLU gate
             else:
-                dx = _conv_forward(dyc, st, None, None, 0, L.ACT_NONE, x.dtype, dgrad=True)
+                dx = _conv_forward(dyc, st, None, None, 0, L.ACT_NONE, x.dtype, dgrad=True, snap=ctx.snap)
                 if ctx.mask_input:
                     g = torch.empty_like(dx)
                     call("icgan_relu_bwd", ptr(dx), ptr(x), ptr(g), dx.numel(), dt(x), dt(g), stream_ptr())
@@ -354,7 +382,7 @@ class SNConvFn(torch.autograd.Function):
                 else:
                     call("icgan_conv2d_wgrad_simt", ptr(x), ptr(dyc), ptr(G), B, H, W, cin, cout, k, 1, k // 2, dt(x),
                          stream_ptr())
-            dW = st.weight_grad(G)
+            dW = st.weight_grad(G, ctx.snap)
         return dx, dW, db, dres, None, None, None, None, None, None, None
 
 
@@ -375,7 +403,7 @@ class SNLinearFn(torch.autograd.Function):
         N = weight.shape[0]
         y = torch.empty(Bn, N, device=x.device, dtype=torch.float32)
         _gemm(x, weight, y, Bn, N, K, (K, 1), (1, K), (N, 1), alpha_dev=st.alpha, bias=bias)  # B[k][n] = W[n][k]
-        ctx.st, ctx.has_bias = st, bias is not None
+        ctx.st, ctx.has_bias, ctx.snap = st, bias is not None, st.snap
         ctx.save_for_backward(x, weight)
         return y
 
@@ -389,11 +417,12 @@ class SNLinearFn(torch.autograd.Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _gemm(dy, weight, dx, Bn, K, N, (N, 1), (K, 1), (K, 1), alpha_dev=st.alpha)  # dx = dy @ (W/sigma)
+            _gemm(dy, weight, dx, Bn, K, N, (N, 1), (K, 1), (K, 1),
+                  alpha_dev=ctx.snap[2][1:] if st.use_sn else None)  # dx = dy @ (W/sigma)
         if ctx.needs_input_grad[1]:
             G = torch.empty(N, K, device=x.device, dtype=torch.float32)
             _gemm(dy, x, G, N, K, Bn, (1, N), (K, 1), (K, 1))  # G = dy^T @ x = dL/d(W/sigma)
-            dW = st.weight_grad(G)
+            dW = st.weight_grad(G, ctx.snap)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.zeros(N, device=x.device, dtype=torch.float32)
             call("icgan_channel_sum", ptr(dy), ptr(db), Bn, N, L.F32, stream_ptr())
@@ -405,7 +434,7 @@ class SNEmbedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, idx, weight, st: SNState):
-        ctx.st = st
+        ctx.st, ctx.snap = st, st.snap
         ctx.save_for_backward(idx)
         rows = weight.detach().index_select(0, idx)
         return rows * st.alpha if st.alpha is not None else rows
@@ -416,7 +445,7 @@ class SNEmbedFn(torch.autograd.Function):
         st: SNState = ctx.st
         G = torch.zeros(st.rows, st.cols, device=dy.device, dtype=torch.float32)
         G.index_add_(0, idx, dy.float())
-        return None, st.weight_grad(G), None
+        return None, st.weight_grad(G, ctx.snap), None
 
 
 # ===================================================================================== batch norm (+ReLU, +up x2)

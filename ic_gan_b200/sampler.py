@@ -42,6 +42,15 @@ class ConditioningSampler:
         self.sample_nns = [np.asarray(r) for r in sample_nns]  # host: only used to draw indices
         if len(self.sample_nns) != f.shape[0]:
             raise ValueError(f"sample_nns has {len(self.sample_nns)} rows, features {f.shape[0]}")
+        # Rectangular table (the make_hdf5_nns output, [N, k]): keep it on the device and draw ALL neighbour positions of a
+        # batch with one vectorised np.random.randint -- the legacy numpy stream yields the same numbers as the
+        # reference's per-instance np.random.choice(row) calls (tests/test_sampler.py pins that), without a Python loop
+        # of B RNG calls on the step's critical path.
+        widths = {len(r) for r in self.sample_nns}
+        self.nn_width = widths.pop() if len(widths) == 1 else None
+        self.nns_dev = None
+        if self.nn_width:
+            self.nns_dev = torch.as_tensor(np.stack(self.sample_nns).astype(np.int64), device=dev)
         self.labels_host = None if labels is None else np.asarray(labels).astype(np.int64)
         self.labels = None if labels is None else torch.as_tensor(self.labels_host, device=dev)
         n = f.shape[0]
@@ -52,8 +61,8 @@ class ConditioningSampler:
         """Rows `index` of the (optionally flip-augmented) feature table, on the device (datasets_common.py:647-679)."""
         idx = np.atleast_1d(np.asarray(index)).astype(np.int64)
         flips = None
-        if self.draw_hflip:  # one draw per instance, in order, as the reference's loop does
-            flips = np.array([np.random.randint(2) == 1 for _ in idx], dtype=bool)
+        if self.draw_hflip:  # one draw per instance, in order, as the reference's loop does (same stream, one call)
+            flips = np.random.randint(2, size=len(idx)) == 1
         ti = torch.as_tensor(idx, device=self.device)
         out = self.feats.index_select(0, ti)
         if self.feature_augmentation and flips is not None and flips.any():
@@ -70,7 +79,15 @@ class ConditioningSampler:
         else:
             sel = np.random.choice(self.possible_sampling_idxs, batch_size, replace=True, p=weights)
         instance_gen = self.get_instance_features(sel)
-        chosen = [np.random.choice(self.sample_nns[i]) for i in sel]  # drawn even without labels, as in the reference
+        # the neighbour is drawn even without labels, as in the reference (it advances the stream)
+        if self.nns_dev is not None:
+            pos = np.random.randint(0, self.nn_width, size=batch_size)
+            if self.labels is None:
+                return None, instance_gen
+            chosen = self.nns_dev[torch.as_tensor(np.asarray(sel, dtype=np.int64), device=self.device),
+                                  torch.as_tensor(pos, device=self.device)]
+            return self.labels.index_select(0, chosen), instance_gen
+        chosen = [np.random.choice(self.sample_nns[i]) for i in sel]  # ragged rows: per-instance draws
         labels_gen = None
         if self.labels is not None:
             labels_gen = self.labels.index_select(0, torch.as_tensor(np.asarray(chosen, dtype=np.int64), device=self.device))

@@ -225,6 +225,21 @@ int icgan_upfirdn2d(const void* x, const float* f, void* y, int N, int C, int in
                     int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                     int channels_last, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step fused with the EMA of the generator.
+ * ---------------------------------------------------------------------------------------------- */
+/* One torch.optim.Adam step (amsgrad off, weight_decay 0, maximize off -- every IC-GAN config; BigGAN_PyTorch/trainer.py:
+ * 158-171, stepped at train_fns.py:115,177) over a FLAT float32 parameter buffer of n elements, `step` = 1-based step count:
+ *   g' = grad*grad_scale; m = lerp(m, g', 1-beta1); v = v*beta2 + (1-beta2)*g'^2; p -= lr/(1-beta1^step) * m / (sqrt(v)/
+ *   sqrt(1-beta2^step) + eps); and, when ema != NULL and ema_decay >= 0, utils.ema.update's rule for the same elements
+ *   (BigGAN_PyTorch/utils.py:1062-1066): ema = ema*ema_decay + p*(1-ema_decay). All buffers 16-byte aligned. */
+int icgan_adam_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
+                        double lr, double beta1, double beta2, double eps, int64_t step, double grad_scale,
+                        double ema_decay, void* stream);
+/* ema = ema*decay + src*(1-decay) over n floats: the non-parameter state entries utils.ema also averages
+ * (BN running statistics, SN u0/sv0; utils.py:1060-1066). */
+int icgan_ema_lerp(float* ema, const float* src, int64_t n, double decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -380,7 +380,7 @@ def train_step(st: StepState, cfg: BigGANConfig, x: Tensor, y: Optional[Tensor],
         g_loss.backward()
     st.opt_g.step()
     if st.ema_sd is not None:  # utils.py:1055-1067: every state_dict entry, decay 0 before ema_start
-        decay = 0.0 if st.itr < ema_start else ema_decay
+        decay = 0.0 if (st.itr and st.itr < ema_start) else ema_decay  # `if itr and itr < start_itr` (utils.py:1058)
         with torch.no_grad():
             for k, v in st.g_sd.items():
                 st.ema_sd[k].copy_(st.ema_sd[k] * decay + v.detach() * (1 - decay))

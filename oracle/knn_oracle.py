@@ -45,3 +45,28 @@ def obtain_nns(x32: np.ndarray, k_nn: int, block: int = 512):
             nns[b0 + r, :min(k_nn, keep.size)] = keep[:k_nn]
             radii[b0 + r] = float(np.sqrt(np.float32(ex[min(kk, ex.size) - 1])))  # float32 sqrt as Faiss' output
     return nns, radii
+
+
+def obtain_nns_rows(x32: np.ndarray, rows, k_nn: int):
+    """The same answer for a subset of query rows only (exact float64 difference form against the whole database):
+    lets tests and bench.py check builds whose full oracle would take hours (N = 100 k ... 1.28 M)."""
+    x32 = np.ascontiguousarray(x32, dtype=np.float32)
+    rows = np.asarray(rows, dtype=np.int64)
+    nns = np.full((rows.size, k_nn), -1, dtype=np.int64)
+    radii = np.zeros(rows.size, dtype=np.float64)
+    n = x32.shape[0]
+    kk = k_nn + 1
+    for o, r in enumerate(rows):
+        q = x32[r].astype(np.float64)
+        ex = np.empty(n, dtype=np.float64)
+        for c0 in range(0, n, 65536):  # chunked: no [N, d] float64 temporary
+            diff = x32[c0:c0 + 65536].astype(np.float64) - q[None, :]
+            ex[c0:c0 + 65536] = (diff * diff).sum(1)
+        m = min(n, kk + 16)
+        cand = np.argpartition(ex, m - 1)[:m]
+        order = np.lexsort((cand, ex[cand]))
+        cand = cand[order][:kk]
+        keep = cand[cand != r]
+        nns[o, :min(k_nn, keep.size)] = keep[:k_nn]
+        radii[o] = float(np.sqrt(np.float32(ex[cand[min(kk, cand.size) - 1]])))
+    return nns, radii

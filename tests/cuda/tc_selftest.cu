@@ -323,6 +323,9 @@ int main(int argc, char** argv) {
         {"p6_192to96@256", 8, 256, 256, 192, 96, 3, 1, 0, 0, 1},
         {"p7_1536@16", 64, 16, 16, 1536, 1536, 3, 1, 0, 0, 1},
         {"p8_768to384@64", 32, 64, 64, 768, 384, 3, 1, 0, 0, 1},
+        // D's first residual conv at BASELINE config 3's micro-batch (2 x 128 images): 1.6 G elements per tensor,
+        // fp32 output = 6.4 GB (byte offsets beyond 32 bits)
+        {"p9_96@256_B256", 256, 256, 256, 96, 96, 3, 0, 0, 0, 1},
     };
     for (const ConvCase& c : perf_cases) fails += run_conv_case(c, true);
     if (convperf) {

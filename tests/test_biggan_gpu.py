@@ -1,28 +1,45 @@
 """Whole-network parity on the GPU: the B200 Generator/Discriminator/G_D against (i) golden vectors frozen from the
 live reference and (ii) the CPU oracle re-run on the same inputs; float32 parity mode and bf16 throughput mode."""
+import json
+import os
+
 import pytest
 import torch
 
 from oracle import biggan_oracle as O
-from tests.helpers import load_golden, make_models, rel_l2
+from tests.helpers import GOLD, load_golden, make_models, rel_l2
 
 pytestmark = pytest.mark.gpu
-CASES = ["ic64_tiny", "cc32_tiny"]
-# images: BASELINE.json bar (<= 1e-3 max-abs vs the fp32 reference) holds in parity mode; bf16 mode has its own bar.
-IMG_TOL = {torch.float32: 1e-3, torch.bfloat16: 6e-2}
-# bf16 mode: activations are rounded to 8 mantissa bits at every layer and float atomics reorder sums run to run, so
-# whole-network gradients agree with the fp32 oracle to a few percent in relative L2 (ic64_tiny: worst parameter
-# 1.4-2.0e-2 over repeated runs); 0-d parameters (attention gamma, a single heavily-cancelling dot product) only to
-# sign/magnitude.  cc32_tiny (|logits| ~ 35 with the synthetic weights) has one heavily cancelling parameter that sits
-# at 0.206-0.209 in every run measured, and one run in about ten went over the previous 0.25 bar, hence 0.30.
-# Parity mode (fp32) is held to 5e-3 (measured 2e-6 ... 4e-5 in the D phase).
-GRAD_TOL = {torch.float32: 5e-3, torch.bfloat16: 0.30}
+# two toy nets + ONE real-width slice of BASELINE config 3 (cc-256, ch 96: 1536-channel layers, 256x256 images, batch 2)
+CASES = ["ic64_tiny", "cc32_tiny", "cc256_w96"]
+# Parity mode (fp32 activations, exact-fp32 kernels): BASELINE.json's bar, <= 1e-3 max-abs on images vs the fp32 reference,
+# gradients <= 5e-3 rel-L2 (measured 2e-6 ... 4e-5).
+# bf16 tensor-core mode: its bars are NOT hand-picked.  tests/golden/biggan_bf16_reference_bound.json holds what bf16 costs
+# the unmodified reference itself (the reference modules under torch.autocast(bfloat16) against their own fp32 run, same
+# weights and inputs, produced by oracle/make_golden_r2.py): image max-abs 1.3-1.8e-2, worst per-parameter gradient
+# rel-L2 0.18-0.26, 0-d parameters up to 5x.  The B200 path may deviate from the fp32 reference by at most BF16_SLACK
+# times what the reference's own bf16 run does (different rounding points and summation orders, same precision).
+with open(os.path.join(GOLD, "biggan_bf16_reference_bound.json")) as _f:
+    BOUND = json.load(_f)
+BF16_SLACK = 2.0  # measured round 1: the B200 path deviates 0.4x-1.0x as much as the reference's own bf16 run
+IMG_TOL_F32, GRAD_TOL_F32, LOGIT_TOL_F32 = 1e-3, 5e-3, 2e-3
 
 
-def _tol(cdt, ref):
-    if cdt == torch.bfloat16 and ref.dim() == 0:
-        return 1.0
-    return GRAD_TOL[cdt]
+def img_tol(cdt, name):
+    return IMG_TOL_F32 if cdt == torch.float32 else BF16_SLACK * BOUND[name]["image_max_abs"]
+
+
+def logit_tol(cdt, name, phase):
+    return LOGIT_TOL_F32 if cdt == torch.float32 else max(0.02, BF16_SLACK * BOUND[name][f"{phase}_logit_max_abs_over_scale"])
+
+
+def grad_tol(cdt, name, phase, ref):
+    if cdt == torch.float32:  # G phase: gradients pass through both networks; one run in three measured 4e-3
+        return GRAD_TOL_F32 * (2 if phase == "g" else 1)
+    b = BOUND[name][f"{phase}_phase_grads"]
+    if ref.dim() == 0:  # a single heavily-cancelling dot product (attention gamma)
+        return max(1.0, BF16_SLACK * b["zero_dim_rel"])
+    return min(1.0, max(0.05, BF16_SLACK * b["worst_rel_l2"]))
 
 
 def _dev(t, dev):
@@ -40,7 +57,7 @@ def test_generator_eval_matches_reference(cuda_device, name, cdt):
     assert out.shape == fx["G_eval_out"].shape and out.dtype == torch.float32
     err = (out.cpu() - fx["G_eval_out"]).abs().max().item()
     print(f"G eval {name} {cdt}: max-abs err vs reference {err:.3e}")
-    assert err <= IMG_TOL[cdt]
+    assert err <= img_tol(cdt, name)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -58,10 +75,11 @@ def test_d_phase_matches_reference(cuda_device, name, cdt):
                         _dev(fx.get("label_r"), dev), fx["feats_r"].to(dev), train_G=False)
     loss = torch.relu(1.0 - d_real).mean() + torch.relu(1.0 + d_fake).mean()
     loss.backward()
-    logit_tol = 2e-3 if cdt == torch.float32 else 0.35
+    lt = logit_tol(cdt, name, "d")
     scale = max(1.0, fx["D_real"].abs().max().item())
-    assert (d_fake.cpu() - fx["D_fake"]).abs().max().item() <= logit_tol * scale
-    assert (d_real.cpu() - fx["D_real"]).abs().max().item() <= logit_tol * scale
+    e_logit = max((d_fake.cpu() - fx["D_fake"]).abs().max().item(), (d_real.cpu() - fx["D_real"]).abs().max().item())
+    print(f"D phase {name} {cdt}: logits max-abs err / scale {e_logit / scale:.3e} (tol {lt:.3e})")
+    assert e_logit <= lt * scale
     # buffers after one training forward: u0 / sv0 / BN running statistics
     for key in [k for k in fx if k.startswith("buf_after_Dphase/")]:
         net, k = key[len("buf_after_Dphase/"):].split(".", 1)
@@ -82,12 +100,14 @@ def test_d_phase_matches_reference(cuda_device, name, cdt):
         if ref.abs().max().item() < 1e-6:  # biases feeding no nonlinearity etc.
             continue
         e = rel_l2(p.grad, ref)
-        worst = max(worst, e)
-        assert e <= _tol(cdt, ref), f"D grad {k}: rel-L2 {e:.3e}"
-    print(f"D phase {name} {cdt}: worst grad rel-L2 {worst:.3e}")
+        if ref.dim() > 0:
+            worst = max(worst, e)
+        assert e <= grad_tol(cdt, name, "d", ref), f"D grad {k}: rel-L2 {e:.3e}"
+    print(f"D phase {name} {cdt}: worst grad rel-L2 {worst:.3e} (reference's own bf16 run: "
+          f"{BOUND[name]['d_phase_grads']['worst_rel_l2']:.3e})")
     for key in [k for k in fx if k.startswith("D_grad/")]:
         got = dict(D.named_parameters())[key[len("D_grad/"):]].grad
-        assert rel_l2(got, fx[key]) <= GRAD_TOL[cdt], key
+        assert rel_l2(got, fx[key]) <= grad_tol(cdt, name, "d", fx[key]), key
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -103,9 +123,9 @@ def test_g_phase_matches_oracle(cuda_device, name, cdt):
     GD = G_D(G, D)
     d_fake = GD(fx["z"].to(dev), _dev(fx.get("label_g"), dev), fx["feats_g"].to(dev), train_G=True)
     (-d_fake.mean()).backward()
-    logit_tol = 2e-3 if cdt == torch.float32 else 0.35
+    lt = logit_tol(cdt, name, "g")
     scale = max(1.0, fx["G_phase_D_fake"].abs().max().item())
-    assert (d_fake.cpu() - fx["G_phase_D_fake"]).abs().max().item() <= logit_tol * scale
+    assert (d_fake.cpu() - fx["G_phase_D_fake"]).abs().max().item() <= lt * scale
     for k, v in g_sd.items():
         if O.is_param(k, v):
             v.requires_grad_(True)
@@ -120,9 +140,11 @@ def test_g_phase_matches_oracle(cuda_device, name, cdt):
         if ref.abs().max().item() < 1e-5 * max(1.0, g_sd[k].abs().max().item()):
             continue  # conv biases followed by batch norm: analytically zero gradient, pure rounding noise
         e = rel_l2(p.grad, ref)
-        worst = max(worst, e)
-        assert e <= _tol(cdt, ref) * 2, f"G grad {k}: rel-L2 {e:.3e}"
-    print(f"G phase {name} {cdt}: worst grad rel-L2 {worst:.3e}")
+        if ref.dim() > 0:
+            worst = max(worst, e)
+        assert e <= grad_tol(cdt, name, "g", ref), f"G grad {k}: rel-L2 {e:.3e}"
+    print(f"G phase {name} {cdt}: worst grad rel-L2 {worst:.3e} (reference's own bf16 run: "
+          f"{BOUND[name]['g_phase_grads']['worst_rel_l2']:.3e})")
 
 
 def test_smoke_step(cuda_device):

@@ -94,3 +94,43 @@ def test_gpu_knn_properties_at_scale(cuda_device):
         order = torch.argsort(dist, stable=True)[: k + 1]
         expect = [j for j in order.tolist() if j != r][:k]
         assert nn[r].tolist() == expect
+
+
+def test_nns_file_roundtrip(tmp_path):
+    """sample_nns / sample_nns_radius on disk: the reference's dataset names, dtypes and shapes (make_hdf5_nns.py:153-172)."""
+    from ic_gan_b200 import knn
+    rng = np.random.default_rng(1)
+    nns = rng.integers(0, 1000, (37, 50))
+    rad = rng.random(37)
+    name = knn.nns_filename(str(tmp_path), 256, "imagenet", "train", False, "selfsupervised", "resnet50", 50)
+    assert name.endswith("ILSVRC256_feats_selfsupervised_resnet50_nn_k50.hdf5")
+    out = knn.save_nns(name, torch.from_numpy(nns), torch.from_numpy(rad))
+    a, b = knn.load_nns(name)
+    assert a.dtype == np.int64 and b.dtype == np.float64 and a.shape == (37, 50) and b.shape == (37,)
+    assert np.array_equal(a, nns) and np.array_equal(b, rad) and os.path.exists(out)
+
+
+def test_oracle_rows_agree_with_full_oracle():
+    meta, x32, data = _golden_features()
+    rows = [0, 3, 7, 900, 901, 1499]
+    nns, radii = K.obtain_nns_rows(x32, rows, meta["k"])
+    assert np.array_equal(nns, data["nns"].astype(np.int64)[rows]) and np.array_equal(radii, data["radii"][rows])
+
+
+@pytest.mark.gpu
+def test_gpu_knn_100k_rows_match_oracle(cuda_device):
+    """BASELINE config 5's oracle-checkable size: N = 100 000, d = 2048, k = 50; every row certified or recomputed on the
+    device, 48 query rows (first/last tiles + random) bit-exact against the float64 oracle."""
+    from ic_gan_b200 import knn
+    n, d, k = 100_000, 2048, 50
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(n, d, generator=g)
+    x32 = K.normalize_features(x.numpy())
+    res = knn.obtain_nns(torch.from_numpy(x32).to(cuda_device), k)
+    print("knn 100k stats", res.stats)
+    rows = np.concatenate([np.arange(8), np.arange(n - 8, n), np.random.default_rng(0).integers(0, n, 32)])
+    want_nn, want_r = K.obtain_nns_rows(x32, rows, k)
+    got_nn = res.sample_nns.cpu().numpy()[rows]
+    got_r = res.sample_nns_radius.cpu().numpy()[rows]
+    assert np.array_equal(got_nn, want_nn)
+    assert np.array_equal(got_r, want_r)

@@ -18,3 +18,14 @@ def test_tc_selftest_binary(cuda_device, env):
     out = subprocess.run([exe, "all"], capture_output=True, text=True, timeout=300, env={**os.environ, **env})
     print(out.stdout[-4000:])
     assert out.returncode == 0 and "TC_SELFTEST PASSED" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_tc_selftest_real_shapes(cuda_device):
+    """Mode `perf`: everything above plus the layer shapes of BASELINE config 3 at real widths and batch (384@64x64 B=32,
+    96@256x256 B=8 and B=256, 1536@8x8/16x16 B=64, 768@32x32, 192@128x128 ...), each verified against the host fp64
+    reference on 6000 sampled outputs and then timed (the timings are informational; the assertion is correctness)."""
+    exe = os.path.join(ROOT, "tests", "cuda", "tc_selftest")
+    out = subprocess.run([exe, "perf"], capture_output=True, text=True, timeout=1200)
+    print(out.stdout[-6000:])
+    assert out.returncode == 0 and "TC_SELFTEST PASSED" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]

@@ -139,11 +139,8 @@ def test_loss_phases_on_cpu_oracle_ops(cpu_ops, phase, seed, gain):
 
 
 # ------------------------------------------------------------------------------------------------------- GPU
-PENDING = pytest.mark.xfail(strict=False, reason="first GPU run pending (modules written after the round's GPU budget)")
-
 
 @pytest.mark.gpu
-@PENDING
 def test_gpu_generator_and_discriminator_fp32(cuda_device):
     meta, fx, _ = _load()
     G, D = _build(meta, cuda_device)
@@ -165,7 +162,6 @@ def test_gpu_generator_and_discriminator_fp32(cuda_device):
 
 
 @pytest.mark.gpu
-@PENDING
 def test_gpu_generator_bf16_blocks(cuda_device):
     """num_fp16_res=2: the two highest resolutions compute in bfloat16 (tensor-core conv path)."""
     meta, fx, _ = _load()
@@ -180,17 +176,26 @@ def test_gpu_generator_bf16_blocks(cuda_device):
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("phase,gain", [("Gmain", 1.0), ("Greg", 4.0), ("Dmain", 1.0), ("Dreg", 16.0)])
 def test_gpu_loss_phases_run_and_match_cpu_oracle(cuda_device, phase, gain):
-    """Device RNG streams differ from the CPU's, so randomness is removed (no style mixing, zero noise strengths) and
-    the path-length noise is injected; gradients are compared with the CPU oracle's on the same inputs."""
+    _phase_vs_oracle(cuda_device, phase, gain, 2e-2)
+
+
+@pytest.mark.parametrize("phase,gain", [("Gmain", 1.0), ("Greg", 4.0), ("Dmain", 1.0), ("Dreg", 16.0)])
+def test_phase_harness_on_cpu_oracle_ops(cpu_ops, phase, gain):
+    """The harness of the GPU test above (shared seeded noise for oracle and modules), exercised on the CPU op oracles."""
+    _phase_vs_oracle(torch.device("cpu"), phase, gain, 2e-3)
+
+
+def _phase_vs_oracle(cuda_device, phase, gain, tol):
+    """Device RNG streams differ from the CPU's, so every random draw (per-layer synthesis noise, path-length noise) comes
+    from ONE seeded CPU generator for both runs (torch.randn / randn_like patched in this test only); style mixing is
+    off (its cutoff only selects a slice).  Gradients -- including noise_strength, which is sum(dy * noise) -- are
+    compared with the CPU oracle's on the same inputs.  (Round 1 zeroed the noise strengths but still compared the
+    noise_strength gradient, which depends on the draw itself: that, not a kernel, made Gmain/Greg fail on the GPU.)"""
     meta, _, _ = _load()
     g_sd = O.synth_state_dict(meta["g_shapes"], meta["g_seed"])
     d_sd = O.synth_state_dict(meta["d_shapes"], meta["d_seed"])
-    for k in g_sd:
-        if k.endswith("noise_strength"):
-            g_sd[k] = torch.zeros_like(g_sd[k])
     cfg = O.StyleGANConfig(**meta["cfg"])
     G, D = _build(meta, cuda_device)
     G.load_state_dict(g_sd); G.train(); D.train()
@@ -199,26 +204,42 @@ def test_gpu_loss_phases_run_and_match_cpu_oracle(cuda_device, phase, gain):
     for k, v in (g_sd if is_g else d_sd).items():
         if v.dtype.is_floating_point and not k.endswith(("resample_filter", "noise_const", "w_avg")):
             v.requires_grad_(True)
-    noise = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(9))
-    orig = torch.randn_like
+    orig, orig_like = torch.randn, torch.randn_like
+    gen = [None]
+
+    def fake_randn(*size, **kw):
+        shape = size[0] if len(size) == 1 and isinstance(size[0], (list, tuple, torch.Size)) else size
+        out = orig(list(shape), generator=gen[0])
+        return out.to(kw["device"]) if kw.get("device") is not None else out
+
+    def fake_randn_like(t, **kw):
+        return orig(list(t.shape), generator=gen[0]).to(device=t.device, dtype=t.dtype)
     try:
-        torch.randn_like = lambda t, **kw: noise.to(t.device) if t.shape == noise.shape else orig(t, **kw)
+        torch.randn, torch.randn_like = fake_randn, fake_randn_like
+        gen[0] = torch.Generator().manual_seed(9)
         O.accumulate_gradients(phase, g_sd, d_sd, cfg, x, None, h, z, None, h, gain, pl_mean=torch.tensor(0.05),
                                style_mixing_prob=0.0)
         loss = b200_loss.StyleGAN2Loss(cuda_device, G.mapping, G.synthesis, D, style_mixing_prob=0.0)
         loss.pl_mean.fill_(0.05)
         G.requires_grad_(is_g); D.requires_grad_(not is_g)
         c0 = torch.zeros(z.shape[0], 0, device=cuda_device)
+        gen[0] = torch.Generator().manual_seed(9)
         loss.accumulate_gradients(phase=phase, real_img=x.to(cuda_device), real_c=c0, real_h=h.to(cuda_device),
                                   gen_z=z.to(cuda_device), gen_c=c0, gen_h=h.to(cuda_device), sync=True, gain=gain)
     finally:
-        torch.randn_like = orig
+        torch.randn, torch.randn_like = orig, orig_like
     net, keys, sd = (G, meta["grad_keys_g"], g_sd) if is_g else (D, meta["grad_keys_d"], d_sd)
     params = dict(net.named_parameters())
-    for k in keys:
+    report = []
+    for k in sorted(params):  # every parameter, not only the golden's key subset
         ref = sd[k].grad
         if ref is None or ref.abs().max() == 0:
             continue
-        got = params[k].grad.cpu()
-        rel = (got - ref).norm() / ref.norm().clamp_min(1e-30)
-        assert rel <= 2e-2, f"{phase} grad {k}: rel-L2 {rel:.3e}"
+        got = params[k].grad
+        assert got is not None, f"{phase}: no gradient for {k}"
+        rel = float((got.cpu() - ref).norm() / ref.norm().clamp_min(1e-30))
+        report.append((rel, k))
+    report.sort(reverse=True)
+    print(f"{phase}: worst gradient rel-L2 vs CPU oracle: " + ", ".join(f"{k} {r:.2e}" for r, k in report[:4]))
+    bad = [(r, k) for r, k in report if r > tol]
+    assert not bad, f"{phase}: {bad[:6]}"
