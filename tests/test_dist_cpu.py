@@ -146,7 +146,7 @@ def test_ema_covers_every_state_entry_and_start_itr():
     assert all(torch.equal(tgt.state_dict()[k], src.state_dict()[k]) for k in src.state_dict())  # initial copy
     with torch.no_grad():
         src.w.fill_(2.0); src.stored_mean.fill_(20.0); src.u0.fill_(200.0)
-    e.update(itr=0)  # before start_itr: decay 0 -> target := source
+    e.update(itr=1)  # before start_itr: decay 0 -> target := source
     assert torch.equal(tgt.w.data, src.w.data) and torch.equal(tgt.stored_mean, src.stored_mean) and torch.equal(tgt.u0, src.u0)
     with torch.no_grad():
         src.w.fill_(3.0); src.stored_mean.fill_(30.0); src.u0.fill_(300.0)
@@ -154,3 +154,10 @@ def test_ema_covers_every_state_entry_and_start_itr():
     assert torch.allclose(tgt.w.data, torch.full((3,), 0.9 * 2.0 + 0.1 * 3.0))
     assert torch.allclose(tgt.stored_mean, torch.full((2,), 0.9 * 20.0 + 0.1 * 30.0))
     assert torch.allclose(tgt.u0, torch.full((1, 4), 0.9 * 200.0 + 0.1 * 300.0))
+    # the reference tests `if itr and itr < start_itr` (utils.py:1058): itr == 0 is falsy and uses the REAL decay
+    # (pinned against the live reference by tests/golden/biggan_step_cc32.*)
+    before = tgt.w.data.clone()
+    with torch.no_grad():
+        src.w.fill_(4.0)
+    e.update(itr=0)
+    assert torch.allclose(tgt.w.data, 0.9 * before + 0.1 * 4.0)
