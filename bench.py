@@ -31,7 +31,7 @@ WORKLOADS = {
     "cc256": dict(name="cc-IC-GAN BigGAN 256x256 (ch96, attn@64, class+instance cond)", resolution=256, ch=96,
                   attn="64", class_cond=True, G_f=146.43, D_f=74.67, per_gpu_batch=256, micro_batch=128),
     "ic128": dict(name="IC-GAN BigGAN 128x128 (ch96, attn@64, instance cond)", resolution=128, ch=96, attn="64",
-                  class_cond=False, G_f=42.26, D_f=21.68, per_gpu_batch=256, micro_batch=64),
+                  class_cond=False, G_f=42.26, D_f=21.68, per_gpu_batch=256, micro_batch=256),
     "ic64": dict(name="IC-GAN BigGAN 64x64 (ch64, attn@32, instance cond)", resolution=64, ch=64, attn="32",
                  class_cond=False, G_f=14.52, D_f=2.23, per_gpu_batch=256, micro_batch=128),
 }
@@ -154,8 +154,7 @@ def oracle_pool_rate(workload, batch, steps, warmup):
     cores = len(avail)
     threads = min(ORACLE_THREADS, cores)
     workers = max(1, cores // threads)
-    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="",
-               OMP_PROC_BIND="close", OMP_PLACES="cores")
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         env.pop(k, None)
     cmd = [sys.executable, os.path.abspath(__file__), "--oracle-worker", "--workload", workload, "--steps", str(steps),

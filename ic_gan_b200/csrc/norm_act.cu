@@ -235,18 +235,20 @@ __global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T
 // out[0] += sum a*b
 template <typename T>
 __global__ void dot_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out, int64_t n) {
-  float s = 0.f;
+  // double accumulation inside the block: the result (attention's d gamma = <dy, o>) is a heavily cancelling sum
+  // (measured at real width: |sum| ~ 1e-4 of sum|.|), float partials lose it; HBM-bound either way
+  double s = 0.0;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    s = fmaf(ld_as_float(a, i), ld_as_float(b, i), s);
+    s = fma(static_cast<double>(ld_as_float(a, i)), static_cast<double>(ld_as_float(b, i)), s);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  __shared__ float part[8];
+  __shared__ double part[8];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
+    double t = 0.0;
     for (int i = 0; i < (blockDim.x >> 5); ++i) t += part[i];
-    atomicAdd(out, t);
+    atomicAdd(out, static_cast<float>(t));
   }
 }
 

@@ -22,16 +22,18 @@ def _load():
 
 
 def _check(tag, got_sd, fx, lr, param_tol_lr, buf_tol=2e-4):
-    worst = 0.0
+    worst, bad = 0.0, []
     for k, v in got_sd.items():
         ref = fx[f"{tag}/{k}"]
         got = sample_of(v.detach().float().cpu())
         err = (got - ref).abs().max().item()
         if O.is_param(k, v):
             worst = max(worst, err / lr)
-            assert err <= param_tol_lr * lr, f"{tag}.{k}: |w - w_ref| = {err:.3e} = {err / lr:.3f} x lr"
-        else:
-            assert err <= buf_tol * max(1.0, ref.abs().max().item()), f"{tag}.{k} (buffer): {err:.3e}"
+            if err > param_tol_lr * lr:
+                bad.append(f"{tag}.{k}: |w - w_ref| = {err / lr:.3f} x lr")
+        elif err > buf_tol * max(1.0, ref.abs().max().item()):
+            bad.append(f"{tag}.{k} (buffer): {err:.3e}")
+    assert not bad, f"{len(bad)} entries off: " + "; ".join(bad[:12])
     return worst
 
 
@@ -116,13 +118,14 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt):
         # direction instead: rel-L2 of (w_after - w_before) against the reference's update, worst tensor printed.
         assert np.allclose(np.array(losses), ref_losses, atol=0.05 * max(1.0, np.abs(ref_losses).max()))
         worst, worst_k = 0.0, ""
+        lr_of = {"G": hp["G_lr"], "D": hp["D_lr"]}
         for tag, net, sd0 in (("G", G, g_sd0), ("D", D, d_sd0)):
             for k, p in net.named_parameters():
                 w0 = sample_of(sd0[k])
                 upd_ref = fx[f"{tag}/{k}"] - w0
                 upd = sample_of(p.detach().float().cpu()) - w0
-                if upd_ref.norm() < 1e-6:
-                    continue
+                if upd_ref.norm() < 0.05 * lr_of[tag] * upd_ref.numel() ** 0.5:
+                    continue  # gradient is rounding noise (e.g. conv biases feeding a batch norm): nothing to compare
                 e = float((upd - upd_ref).norm() / upd_ref.norm())
                 if e > worst:
                     worst, worst_k = e, f"{tag}.{k}"
