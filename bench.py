@@ -379,6 +379,238 @@ def run_knn(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------- StyleGAN2 (config 4)
+SG = dict(z_dim=512, w_dim=512, h_dim=2048, res=256, channel_base=16384, channel_max=512, map_layers=2, num_fp16_res=4,
+          conv_clamp=256, mbstd=4, G_f=29.79, D_f=30.75, G_reg=4, D_reg=16, lr=0.0025)
+# conv GFLOP per image and iteration: Gmain 3 G_f + 2 D_f, Dmain G_f + 6 D_f, + lazy regularisers
+SG_STEP_GF = 4 * SG["G_f"] + 8 * SG["D_f"] + (2.5 * SG["G_f"]) / 4 + (5 * SG["D_f"]) / 16
+
+
+def sg_build(dev):
+    from ic_gan_b200.stylegan2 import networks as N
+    G = N.Generator(z_dim=SG["z_dim"], c_dim=0, h_dim=SG["h_dim"], w_dim=SG["w_dim"], img_resolution=SG["res"], img_channels=3,
+                    mapping_kwargs=dict(num_layers=SG["map_layers"]),
+                    synthesis_kwargs=dict(channel_base=SG["channel_base"], channel_max=SG["channel_max"],
+                                          num_fp16_res=SG["num_fp16_res"], conv_clamp=SG["conv_clamp"]))
+    D = N.Discriminator(c_dim=0, h_dim=SG["h_dim"], img_resolution=SG["res"], img_channels=3, channel_base=SG["channel_base"],
+                        channel_max=SG["channel_max"], num_fp16_res=SG["num_fp16_res"], conv_clamp=SG["conv_clamp"],
+                        epilogue_kwargs=dict(mbstd_group_size=SG["mbstd"]))
+    return G.to(dev), D.to(dev)
+
+
+def sg_cpu_rate(batch=2):
+    """images/s of the oracle's StyleGAN2 iteration (CPU restatement of loss.py:85-194 over networks.py) at 256x256:
+    one Gmain + one Dmain + Greg/4 + Dreg/16, each phase timed once at `batch`, all host threads."""
+    from oracle import stylegan_nets_oracle as O
+    G, D = sg_build("cpu")
+    cfg = O.StyleGANConfig(z_dim=SG["z_dim"], h_dim=SG["h_dim"], w_dim=SG["w_dim"], img_resolution=SG["res"],
+                           channel_base=SG["channel_base"], channel_max=SG["channel_max"], map_layers=SG["map_layers"],
+                           d_map_layers=8, conv_clamp=float(SG["conv_clamp"]), mbstd_group_size=min(SG["mbstd"], batch))
+    g_sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    d_sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    z, h = torch.randn(batch, SG["z_dim"], generator=g), torch.randn(batch, SG["h_dim"], generator=g)
+    x = torch.rand(batch, 3, SG["res"], SG["res"], generator=g) * 2 - 1
+    times = {}
+    for phase in ("Gmain", "Dmain", "Greg", "Dreg"):
+        sd = g_sd if phase.startswith("G") else d_sd
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and not k.endswith(("resample_filter", "noise_const", "w_avg")):
+                v.requires_grad_(True)
+        t0 = time.perf_counter()
+        O.accumulate_gradients(phase, g_sd, d_sd, cfg, x, None, h, z, None, h, 1.0, pl_mean=torch.tensor(0.0))
+        times[phase] = time.perf_counter() - t0
+        for v in sd.values():
+            v.requires_grad_(False)
+            v.grad = None
+    it = times["Gmain"] + times["Dmain"] + times["Greg"] / SG["G_reg"] + times["Dreg"] / SG["D_reg"]
+    return batch / it, it, times
+
+
+def run_sg256(args):
+    """BASELINE config 4: one StyleGAN2-ADA IC-GAN training iteration at 256x256, 64 images per GPU (training_loop.py:
+    395-535 schedule: Gmain and Dmain every iteration, Greg every 4th, Dreg every 16th, lazy-regularisation-scaled Adam,
+    G_ema) on the B200 networks / loss.  --steps should be a multiple of 16 so that every regulariser is averaged in."""
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "images/sec G+D iteration, IC-GAN StyleGAN2-ADA 256x256"
+    if args.impl == "reference":
+        if rank:
+            return
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        torch.set_num_threads(cores)
+        ips, it, times = sg_cpu_rate(2)
+        sample = ("oracle iteration (CPU restatement of training/loss.py:85-194 over training/networks.py), fp32, batch 2: "
+                  + ", ".join(f"{k} {v:.1f} s" for k, v in times.items()) + f"; iteration = Gmain + Dmain + Greg/4 + Dreg/16 = {it:.1f} s")
+        emit({"impl": "reference", "metric": metric, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": it * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "f32", "data": "synthetic", "config": {"workload": "IC-GAN StyleGAN2-ADA 256x256", "batch": 2,
+                                                               "host_threads": cores},
+              "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+              "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
+    from ic_gan_b200 import _lib, ops
+    from ic_gan_b200.optim import FusedAdamEMA
+    from ic_gan_b200.stylegan2 import loss as sg_loss
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("ICGAN_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        sys.stdout.flush()
+        JSON_OUT[0] = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    torch.manual_seed(4321)
+    Bg = args.per_gpu_batch or 64
+    G, D = sg_build(dev)
+    G_ema, _ = sg_build(dev)
+    G_ema.load_state_dict(G.state_dict())
+    G.train(); D.train(); G_ema.eval()
+    if world > 1:
+        for net in (G, D):
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t.data, src=0)
+
+    def lazy(interval):  # training_loop.py:332-339: Adam hyper-parameters rescaled for lazy regularisation
+        r = interval / (interval + 1)
+        return dict(lr=SG["lr"] * r, betas=(0.0 ** r, 0.99 ** r), eps=1e-8)
+    opt_G = FusedAdamEMA(G.parameters(), **lazy(SG["G_reg"]))
+    opt_D = FusedAdamEMA(D.parameters(), **lazy(SG["D_reg"]))
+    loss = sg_loss.StyleGAN2Loss(dev, G.mapping, G.synthesis, D, augment_pipe=None, style_mixing_prob=0.9,
+                                 r1_gamma=0.0002 * SG["res"] ** 2 / (Bg * world), pl_batch_shrink=2, pl_decay=0.01, pl_weight=2)
+    ema_beta = 0.5 ** (Bg * world / max(Bg * world * 10 / 32 * 1000, 1e-8))  # training_loop.py:528-531, cfg auto ema
+    g_params, e_params = list(G.parameters()), list(G_ema.parameters())
+    g_bufs, e_bufs = list(G.buffers()), list(G_ema.buffers())
+    gen = torch.Generator(device=dev).manual_seed(300 + rank)
+    real_dev = torch.randint(0, 256, (Bg, 3, SG["res"], SG["res"]), device=dev, generator=gen, dtype=torch.uint8)
+    h_dev = torch.randn(Bg, SG["h_dim"], device=dev, generator=gen)
+    c0 = torch.zeros(Bg, 0, device=dev)
+    it_count = [0]
+
+    def iteration(real_u8, real_h):
+        it = it_count[0]
+        it_count[0] += 1
+        real_img = real_u8.to(torch.float32) / 127.5 - 1  # training_loop.py:436
+        gen_z = torch.randn(Bg, SG["z_dim"], device=dev)
+        gen_h = real_h[torch.randperm(Bg, device=dev)]
+        phases = [("Gmain", G, opt_G, 1), ("Greg", G, opt_G, SG["G_reg"]), ("Dmain", D, opt_D, 1), ("Dreg", D, opt_D, SG["D_reg"])]
+        for name, module, opt, interval in phases:
+            if it % interval:
+                continue
+            opt.zero_grad()
+            module.requires_grad_(True)
+            loss.accumulate_gradients(phase=name, real_img=real_img, real_c=c0, real_h=real_h, gen_z=gen_z, gen_c=c0,
+                                      gen_h=gen_h, sync=True, gain=interval)
+            module.requires_grad_(False)
+            if world > 1:
+                dist.all_reduce(opt.flat_g)
+                opt.set_grad_scale(1.0 / world)
+            torch.nan_to_num(opt.flat_g, nan=0, posinf=1e5, neginf=-1e5, out=opt.flat_g)  # training_loop.py:516-521
+            opt.step()
+        with torch.no_grad():  # G_ema (training_loop.py:527-535)
+            torch._foreach_lerp_(e_params, g_params, 1.0 - ema_beta)
+            torch._foreach_copy_(e_bufs, g_bufs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.ncu:
+        args.no_e2e = args.no_cpu_baseline = True
+    for i in range(args.warmup if args.ncu else max(args.warmup, 3)):
+        iteration(real_dev, h_dev)
+    it_count[0] = 0
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE = [] if rank == 0 else None
+    launches0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        iteration(real_dev, h_dev)
+    e1.record()
+    barrier()
+    launches = _lib.LAUNCHES - launches0
+    prof, ops.PROFILE = ops.PROFILE, None
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    e2e = None
+    if not args.no_e2e:
+        cpu_gen = torch.Generator().manual_seed(400 + rank)
+        real_host = torch.randint(0, 256, (Bg, 3, SG["res"], SG["res"]), generator=cpu_gen, dtype=torch.uint8).pin_memory()
+        h_host = torch.randn(Bg, SG["h_dim"], generator=cpu_gen).pin_memory()
+        it_count[0] = 0
+
+        def step_host():
+            iteration(real_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True))
+            return float(loss.stats["Loss/G/loss"]) + float(loss.stats["Loss/D/loss_gen"])  # host read of the losses
+        step_host()
+        it_count[0] = 0
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_host()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": Bg * world / (float(t.item()) * 1e-3), "unit": "images/s", "ms_per_step": float(t.item()),
+               "h2d_bytes_per_step": real_host.numel() + h_host.numel() * 4, "d2h_bytes_per_step": 8}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    per = {}
+    for name, flops, a, b, _ in prof:
+        d = per.setdefault(name, [0.0, 0.0, 0])
+        d[0] += flops; d[1] += a.elapsed_time(b) * 1e-3; d[2] += 1
+    kinfo = {k: {"launches": v[2], "avg_ms": v[1] / v[2] * 1e3, "tflops": v[0] / v[1] * 1e-12,
+                 "share_of_step": v[1] / (ms * 1e-3 * args.steps)} for k, v in per.items()}
+    dom = max(per, key=lambda k: per[k][1]) if per else None
+    roofline = None
+    if dom:
+        ach = per[dom][0] / per[dom][1] * 1e-12
+        roofline = {"kernel": {"sg2_conv": "tc_conv_halo_kernel + tc_conv_kernel (stride 1/2, transposed phases; forward and dgrad)",
+                               "sg2_wgrad": "tc_wgrad_kernel + tc_wgrad_halo_kernel"}[dom], "bound": "tensor", "achieved": ach,
+                    "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                    "peak_source": pk["source"] + ", sustained", "flops_per_launch": per[dom][0] / per[dom][2],
+                    "kernels": kinfo}
+    value = Bg * world / (ms * 1e-3)
+    step_tf = SG_STEP_GF * 1e9 * value / world * 1e-12
+    line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "IC-GAN StyleGAN2-ADA 256x256 (cfg auto: channel_base 16384, map 2, num_fp16_res 4 -> bf16, "
+                                   "conv_clamp 256, mbstd 4, h_dim 2048; fp32 blocks on split-bf16 tensor-core passes)",
+                       "per_gpu_batch": Bg, "global_batch": Bg * world, "parallelism": f"dp{world}",
+                       "schedule": "Gmain + Dmain every iteration, Greg every 4th, Dreg every 16th (lazy regularisation), "
+                                   "fused Adam, G_ema", "l2": "inputs larger than L2",
+                       "step_gflop_per_image": SG_STEP_GF, "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
+            "roofline": roofline,
+            "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        torch.set_num_threads(cores)
+        ips, it, times = sg_cpu_rate(2)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": "oracle iteration at batch 2 (Gmain + Dmain + Greg/4 + Dreg/16 = %.1f s)" % it}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------- B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -386,7 +618,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cc256", choices=sorted(WORKLOADS) + ["knn"])
+    ap.add_argument("--workload", default="cc256", choices=sorted(WORKLOADS) + ["knn", "sg256"])
     ap.add_argument("--knn-n", type=int, default=1281167, help="database rows of --workload knn")
     ap.add_argument("--per-gpu-batch", type=int, default=0)
     ap.add_argument("--micro-batch", type=int, default=0)
@@ -402,6 +634,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "knn":
         return run_knn(args)
+    if args.workload == "sg256":
+        return run_sg256(args)
     w = dict(WORKLOADS[args.workload])
     if args.per_gpu_batch:
         w["per_gpu_batch"] = args.per_gpu_batch

@@ -32,6 +32,9 @@ class IcganSnLayer(C.Structure):
 # name -> argtypes (all return int). Mirrors include/icgan_b200.h one to one; tests check the two stay in sync.
 SIGNATURES = {
     "icgan_conv2d_tc": [vp, vp, fp, fp, vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "icgan_conv2d_tc_ex": [vp, vp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+                           i32, i32, i32, i32, vp],
+    "icgan_conv2d_wgrad_tc_ex": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
     "icgan_conv2d_rgb_tc": [vp, vp, fp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_tc": [vp, vp, fp, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_simt": [vp, fp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
@@ -67,6 +70,11 @@ SIGNATURES = {
     "icgan_bias_act": [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, f32, f32, f32, i32, vp],
     "icgan_upfirdn2d": [vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
                         i32, vp],
+    "icgan_upfirdn2d_nhwc": [vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, fp, fp, fp, i32, fp, i32,
+                             f32, f32, f32, fp, vp, i32, vp],
+    "icgan_modulate": [vp, fp, vp, i32, i64, i32, i32, i32, vp],
+    "icgan_chan_dot": [vp, vp, fp, i32, i64, i32, i32, i32, vp],
+    "icgan_bias_act_nhwc": [vp, vp, vp, fp, fp, fp, fp, i32, i32, i64, i32, i32, i32, f32, f32, f32, i32, vp],
     "icgan_adam_ema_step": [fp, fp, fp, fp, fp, i64, f64, f64, f64, f64, i64, f64, f64, vp],
     "icgan_ema_lerp": [fp, fp, i64, f64, vp],
     "icgan_gemm_tc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
@@ -110,6 +118,11 @@ def call(name: str, *args) -> None:
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {last_error()}")
+
+
+def int_array(values):
+    """Host int array argument (the tap tables of icgan_conv2d_tc_ex / icgan_conv2d_wgrad_tc_ex)."""
+    return (C.c_int * len(values))(*[int(v) for v in values])
 
 
 def stream_ptr() -> int:

@@ -47,8 +47,10 @@ static EncodeTiledFn encode_fn() {
 }
 
 // bf16 tensor, dims[0] fastest. strides_bytes[i] is the stride of dims[i+1].
+// elem_strides (optional): TMA traversal stride per dimension -- with stride s a box spanning box[i] tensor elements
+// delivers ceil(box[i] / s) of them (every s-th), which is how the stride-2 convolutions read their input.
 static int make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                          const uint32_t* box, uint32_t swizzle_bytes) {
+                          const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = encode_fn();
   ICGAN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[5];
@@ -57,7 +59,7 @@ static int make_tmap_bf16(CUtensorMap* m, const void* ptr, int rank, const uint6
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -249,6 +251,11 @@ struct TcConvParams {
   const void* res;
   const float* alpha;  // device scalar multiplied into the accumulator (1/sigma of spectral norm), may be null
   float* stats;        // optional [2*Cout]: += sum_p (y - bias), += sum_p (y - bias)^2 of the (pre-rounding) outputs
+  // Generalised tap list (icgan_conv2d_tc_ex): tile-domain pixel (h, w) reads input pixel (h*in_stride + tdh[t],
+  // w*in_stride + tdw[t]) against weight slice twi[t], and is written to output pixel (h*osy + ooy, w*osx + oox) of an
+  // [B, OH, OW, Cout] tensor.  Plain convolutions: tdh/tdw = -pad..pad, twi[t] = t, in_stride = os* = 1, oo* = 0.
+  int8_t tdh[16], tdw[16], twi[16];
+  int in_stride, OH, OW, osy, ooy, osx, oox;
 };
 
 struct TileCoord {
@@ -321,7 +328,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t chunk_tx = p.a_bytes + p.b_tx;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        int tap = 0, cc = 0, dh = -p.pad, dw = -p.pad, left = p.k_iters;
+        int tap = 0, cc = 0, left = p.k_iters;
+        const int wbase = t.w0 * p.in_stride, hbase = t.h0 * p.in_stride;
         for (int it = 0; it < p.n_stage_iters; ++it) {
           const int n = left < p.G ? left : p.G;
           left -= n;
@@ -332,18 +340,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(n) * chunk_tx);
           for (int g = 0; g < n; ++g) {
             if (leader) {
-              tma_load_4d(sa, &tmA, &full[stage], cc * p.cw, t.w0 + dw, t.h0 + dh, t.n0);
-              tma_load_3d(sb, &tmB, &full[stage], cc * p.cw, tap, t.co0);
+              tma_load_4d(sa, &tmA, &full[stage], cc * p.cw, wbase + p.tdw[tap], hbase + p.tdh[tap], t.n0);
+              tma_load_3d(sb, &tmB, &full[stage], cc * p.cw, p.twi[tap], t.co0);
             }
             sa += p.a_bytes;
             sb += p.b_chunk;
             if (++cc == p.chunks) {
               cc = 0;
               ++tap;
-              if (++dw > p.pad) {
-                dw = -p.pad;
-                ++dh;
-              }
             }
           }
           __syncwarp();
@@ -412,8 +416,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n = t.n0 + nl, h = t.h0 + hl, w = t.w0 + wl;
-      const bool valid = (n < p.B) && (h < p.H) && (w < p.W);
-      const int64_t pix = (static_cast<int64_t>(n) * p.H + h) * p.W + w;
+      const int oy = h * p.osy + p.ooy, ox = w * p.osx + p.oox;
+      const bool valid = (n < p.B) && (h < p.H) && (w < p.W) && (oy < p.OH) && (ox < p.OW);
+      const int64_t pix = (static_cast<int64_t>(n) * p.OH + oy) * p.OW + ox;
       int64_t rpix = pix;
       if (p.res_shift == 1) rpix = (static_cast<int64_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
       mbar_wait(&tfull[acc], acc_phase);
@@ -1029,6 +1034,9 @@ struct TcWgradParams {
   int ci_per_tile, stages;
   uint32_t a_bytes, box_bytes, stage_bytes;
   float* dwk;
+  // generalised taps (icgan_conv2d_wgrad_tc_ex): tap t pairs dY pixel (h, w) with X pixel (h*in_stride + tdh[t], ...)
+  int8_t tdh[16], tdw[16];
+  int in_stride;
 };
 
 static constexpr int kWgradKP = 64;      // pixels (reduction rows) per pipeline stage
@@ -1111,7 +1119,6 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
       uint32_t phase = 0;
       const uint32_t tx = p.a_bytes + static_cast<uint32_t>(nb) * p.box_bytes;
       int tw = kc_begin % p.tiles_w, th = (kc_begin / p.tiles_w) % p.tiles_h, tb = kc_begin / (p.tiles_w * p.tiles_h);
-      const int dh0 = p.taps > 1 ? tap0 / p.ksz - p.pad : 0, dw0 = p.taps > 1 ? tap0 % p.ksz - p.pad : 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
         const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tb * p.TN;
         if (++tw == p.tiles_w) {
@@ -1129,18 +1136,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
           tma_load_4d(sa + p.box_bytes, &tmDy, &full[stage], co0 + 64, w0, h0, n0);
           uint8_t* sb = sa + p.a_bytes;
           if (p.taps > 1) {
-            int dh = dh0, dw = dw0;
             for (int j = 0; j < nb; ++j) {
-              tma_load_4d(sb, &tmX, &full[stage], ci0, w0 + dw, h0 + dh, n0);
+              tma_load_4d(sb, &tmX, &full[stage], ci0, w0 * p.in_stride + p.tdw[tap0 + j],
+                          h0 * p.in_stride + p.tdh[tap0 + j], n0);
               sb += p.box_bytes;
-              if (++dw > p.pad) {
-                dw = -p.pad;
-                ++dh;
-              }
             }
           } else {
             for (int j = 0; j < nb; ++j) {
-              tma_load_4d(sb, &tmX, &full[stage], ci0 + 64 * j, w0, h0, n0);
+              tma_load_4d(sb, &tmX, &full[stage], ci0 + 64 * j, w0 * p.in_stride + p.tdw[0],
+                          h0 * p.in_stride + p.tdh[0], n0);
               sb += p.box_bytes;
             }
           }
@@ -1498,6 +1502,12 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   p.res_shift = res_shift;
   p.act = act;
   p.y = y; p.bias = bias; p.res = residual; p.alpha = alpha_dev; p.stats = bn_stats;
+  for (int t = 0; t < p.taps; ++t) {
+    p.tdh[t] = static_cast<int8_t>(t / ksize - p.pad);
+    p.tdw[t] = static_cast<int8_t>(t % ksize - p.pad);
+    p.twi[t] = static_cast<int8_t>(t);
+  }
+  p.in_stride = 1; p.OH = H; p.OW = W; p.osy = p.osx = 1; p.ooy = p.oox = 0;
   ICGAN_REQUIRE(!bn_stats || (act == ICGAN_ACT_NONE && Cout % 32 == 0),
                 "icgan_conv2d_tc: bn_stats needs act=none and Cout a multiple of 32 (got %d)", Cout);
 
@@ -1525,6 +1535,180 @@ extern "C" int icgan_conv2d_tc(const void* x, const void* wk, const float* alpha
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (bn_stats) tc_conv_kernel<4><<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   else tc_conv_kernel<8><<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Tile shape (TW x TH x TN = `pixels`, powers of two) that wastes the fewest padded pixels over a Wd x Hd x B domain.
+static void choose_tile(int Wd, int Hd, int B, int pixels, int max_w, int* TW, int* TH, int* TN) {
+  double best = 1e30;
+  for (int tw = 1; tw <= pixels && tw <= max_w; tw *= 2)
+    for (int th = 1; tw * th <= pixels; th *= 2) {
+      const int tn = pixels / (tw * th);
+      if (tw > 2 * Wd && tw > 8) continue;
+      const double vol = static_cast<double>(ceil_div(Wd, tw)) * tw * ceil_div(Hd, th) * th * ceil_div(B, tn) * tn;
+      // prefer wide rows at equal volume (longer contiguous runs per TMA box row)
+      const double cost = vol * (1.0 + 0.001 * th + 0.002 * tn);
+      if (cost < best) {
+        best = cost;
+        *TW = tw; *TH = th; *TN = tn;
+      }
+    }
+}
+
+extern "C" int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* bias, const void* residual, void* y, int B,
+                                  int H, int W, int Cin, int Cout, int wtaps, int ntaps, const int* tap_dh,
+                                  const int* tap_dw, const int* tap_w, int in_stride, int Hd, int Wd, int OH, int OW,
+                                  int osy, int ooy, int osx, int oox, int out_dtype, int res_dtype, void* stream) {
+  ICGAN_REQUIRE(x && wk && y && tap_dh && tap_dw && tap_w, "icgan_conv2d_tc_ex: null pointer");
+  ICGAN_REQUIRE(ntaps >= 1 && ntaps <= 16 && wtaps >= 1 && wtaps <= 127, "icgan_conv2d_tc_ex: 1..16 taps (got %d)", ntaps);
+  ICGAN_REQUIRE(in_stride == 1 || in_stride == 2, "icgan_conv2d_tc_ex: input stride 1 or 2 (got %d)", in_stride);
+  ICGAN_REQUIRE(B > 0 && H > 0 && W > 0 && Hd > 0 && Wd > 0 && OH > 0 && OW > 0, "icgan_conv2d_tc_ex: bad shape");
+  ICGAN_REQUIRE(Cin % 16 == 0 && Cin >= 16, "icgan_conv2d_tc_ex: Cin must be a multiple of 16 (got %d)", Cin);
+  ICGAN_REQUIRE(Cout % 8 == 0 && Cout >= 8, "icgan_conv2d_tc_ex: Cout must be a multiple of 8 (got %d)", Cout);
+  ICGAN_REQUIRE(osy >= 1 && osx >= 1 && ooy >= 0 && oox >= 0, "icgan_conv2d_tc_ex: bad output mapping");
+  TcConvParams p{};
+  p.B = B; p.H = Hd; p.W = Wd; p.Cout = Cout;
+  p.ksz = 0; p.pad = 0; p.taps = ntaps;
+  for (int t = 0; t < ntaps; ++t) {
+    ICGAN_REQUIRE(tap_dh[t] >= -64 && tap_dh[t] <= 64 && tap_dw[t] >= -64 && tap_dw[t] <= 64 && tap_w[t] >= 0 &&
+                  tap_w[t] < wtaps, "icgan_conv2d_tc_ex: tap %d out of range", t);
+    p.tdh[t] = static_cast<int8_t>(tap_dh[t]);
+    p.tdw[t] = static_cast<int8_t>(tap_dw[t]);
+    p.twi[t] = static_cast<int8_t>(tap_w[t]);
+  }
+  p.in_stride = in_stride; p.OH = OH; p.OW = OW; p.osy = osy; p.ooy = ooy; p.osx = osx; p.oox = oox;
+  choose_tile(Wd, Hd, B, 128, 128, &p.TW, &p.TH, &p.TN);
+  p.tiles_w = ceil_div(Wd, p.TW);
+  p.tiles_h = ceil_div(Hd, p.TH);
+  const int tiles_b = ceil_div(B, p.TN);
+  p.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  p.swz = static_cast<uint32_t>(p.cw * 2);
+  p.chunks = Cin / p.cw;
+  p.k_iters = p.taps * p.chunks;
+  if (Cout <= 256) p.BN = (Cout + 15) / 16 * 16;
+  else if (Cout % 256 == 0) p.BN = 256;
+  else if (Cout % 192 == 0) p.BN = 192;
+  else if (Cout % 128 == 0) p.BN = 128;
+  else p.BN = 256;
+  p.n_tiles = ceil_div(Cout, p.BN);
+  p.total_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
+  p.a_bytes = 128u * p.swz;
+  p.b_tx = static_cast<uint32_t>(p.BN) * p.swz;
+  p.b_chunk = (p.b_tx + 1023u) & ~1023u;
+  const uint32_t chunk_bytes = p.a_bytes + p.b_chunk;
+  int G = static_cast<int>(49152u / chunk_bytes);
+  if (G < 1) G = 1;
+  if (G > 8) G = 8;
+  if (G > p.k_iters) G = p.k_iters;
+  p.G = G;
+  p.n_stage_iters = (p.k_iters + G - 1) / G;
+  p.stage_bytes = static_cast<uint32_t>(G) * chunk_bytes;
+  const uint32_t tail = 1024u + 512u + 4u * 32u * 33u * 4u;
+  int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  ICGAN_REQUIRE(stages >= 2, "icgan_conv2d_tc_ex: tile does not fit shared memory");
+  p.stages = stages;
+  p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.BN));
+  p.out_bf16 = out_dtype == ICGAN_BF16;
+  p.res_bf16 = res_dtype == ICGAN_BF16;
+  p.res_shift = 0;
+  p.act = ICGAN_ACT_NONE;
+  p.y = y; p.bias = bias; p.res = residual; p.alpha = nullptr; p.stats = nullptr;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    // stride 2: a box spanning 2*T-1 tensor elements delivers T of them (every second one)
+    const uint32_t bw = in_stride == 1 ? (uint32_t)p.TW : (uint32_t)(2 * p.TW - 1);
+    const uint32_t bh = in_stride == 1 ? (uint32_t)p.TH : (uint32_t)(2 * p.TH - 1);
+    const uint32_t box[4] = {(uint32_t)p.cw, bw, bh, (uint32_t)p.TN};
+    const uint32_t es[4] = {1u, (uint32_t)in_stride, (uint32_t)in_stride, 1u};
+    int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, p.swz, es);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)wtaps, (uint64_t)Cout};
+    const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)wtaps * Cin * 2};
+    const uint32_t box[3] = {(uint32_t)p.cw, 1u, (uint32_t)p.BN};
+    int rc = make_tmap_bf16(&tmB, wk, 3, dims, str, box, p.swz);
+    if (rc) return rc;
+  }
+  const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  tc_conv_kernel<8><<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_conv2d_wgrad_tc_ex(const void* a, const void* b, float* out, int B, int Ha, int Wa, int Ca, int Hb,
+                                        int Wb, int Cb, int ntaps, const int* tap_dh, const int* tap_dw, int in_stride,
+                                        void* stream) {
+  ICGAN_REQUIRE(a && b && out && tap_dh && tap_dw, "icgan_conv2d_wgrad_tc_ex: null pointer");
+  ICGAN_REQUIRE(ntaps >= 1 && ntaps <= 16, "icgan_conv2d_wgrad_tc_ex: 1..16 taps (got %d)", ntaps);
+  ICGAN_REQUIRE(in_stride == 1 || in_stride == 2, "icgan_conv2d_wgrad_tc_ex: stride 1 or 2 (got %d)", in_stride);
+  ICGAN_REQUIRE(Cb % 16 == 0 && Ca % 8 == 0, "icgan_conv2d_wgrad_tc_ex: need Cb%%16==0, Ca%%8==0 (got %d, %d)", Cb, Ca);
+  TcWgradParams p{};
+  p.Cin = Cb; p.Cout = Ca; p.ksz = 0; p.pad = 0; p.taps = ntaps;
+  for (int t = 0; t < ntaps; ++t) {
+    p.tdh[t] = static_cast<int8_t>(tap_dh[t]);
+    p.tdw[t] = static_cast<int8_t>(tap_dw[t]);
+  }
+  p.in_stride = in_stride;
+  choose_tile(Wa, Ha, B, kWgradKP, kWgradKP, &p.TW, &p.TH, &p.TN);
+  p.tiles_w = ceil_div(Wa, p.TW);
+  p.tiles_h = ceil_div(Ha, p.TH);
+  p.tiles_b = ceil_div(B, p.TN);
+  p.k_chunks = p.tiles_w * p.tiles_h * p.tiles_b;
+  if (p.taps > 1) {
+    p.ci_per_tile = 64;
+    p.groups = ceil_div(p.taps, kWgradMaxBoxes);
+  } else {
+    p.ci_per_tile = 64 * kWgradMaxBoxes;
+    p.groups = 1;
+  }
+  p.co_tiles = ceil_div(Ca, 128);
+  p.ci_tiles = ceil_div(Cb, p.ci_per_tile);
+  p.box_bytes = static_cast<uint32_t>(kWgradKP) * 128u;
+  p.a_bytes = 2u * p.box_bytes;
+  p.stage_bytes = p.a_bytes + static_cast<uint32_t>(kWgradMaxBoxes) * p.box_bytes;
+  const uint32_t tail = 1024u + 512u;
+  int stages = static_cast<int>((kSmemBudget - tail) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const int out_tiles = p.co_tiles * p.ci_tiles * p.groups;
+  p.splits = choose_splits(out_tiles, p.k_chunks);
+  p.dwk = out;
+  CUtensorMap tmA, tmB;
+  {
+    const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    const uint64_t dims[4] = {(uint64_t)Ca, (uint64_t)Wa, (uint64_t)Ha, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Ca * 2, (uint64_t)Wa * Ca * 2, (uint64_t)Ha * Wa * Ca * 2};
+    int rc = make_tmap_bf16(&tmA, a, 4, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint32_t bw = in_stride == 1 ? (uint32_t)p.TW : (uint32_t)(2 * p.TW - 1);
+    const uint32_t bh = in_stride == 1 ? (uint32_t)p.TH : (uint32_t)(2 * p.TH - 1);
+    const uint32_t box[4] = {64u, bw, bh, (uint32_t)p.TN};
+    const uint32_t es[4] = {1u, (uint32_t)in_stride, (uint32_t)in_stride, 1u};
+    const uint64_t dims[4] = {(uint64_t)Cb, (uint64_t)Wb, (uint64_t)Hb, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cb * 2, (uint64_t)Wb * Cb * 2, (uint64_t)Hb * Wb * Cb * 2};
+    int rc = make_tmap_bf16(&tmB, b, 4, dims, str, box, 128, es);
+    if (rc) return rc;
+  }
+  const uint32_t smem_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes + tail;
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured)) {
+    ICGAN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  }
+  const int grid = out_tiles * p.splits;
+  tc_wgrad_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -1612,6 +1796,11 @@ extern "C" int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, 
     p.splits = choose_splits(out_tiles, p.k_chunks);
   }
   p.dwk = dwk;
+  for (int t = 0; t < p.taps; ++t) {
+    p.tdh[t] = static_cast<int8_t>(t / ksize - p.pad);
+    p.tdw[t] = static_cast<int8_t>(t % ksize - p.pad);
+  }
+  p.in_stride = 1;
 
   CUtensorMap tmDy, tmX;
   const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};

@@ -41,6 +41,8 @@ class StyleGAN2Loss(Loss):
         self.style_mixing_prob, self.r1_gamma = style_mixing_prob, r1_gamma
         self.pl_batch_shrink, self.pl_decay, self.pl_weight = pl_batch_shrink, pl_decay, pl_weight
         self.pl_mean = torch.zeros([], device=device)
+        self.stats = {}  # last value of each reported loss term (0-d device tensors; the reference hands these to
+        #                  training_stats.report, loss.py:101-103,120-122,...): what a trainer reads back per iteration
 
     def run_G(self, z, c, h, sync):
         with _ddp_sync(self.G_mapping, sync):
@@ -70,6 +72,7 @@ class StyleGAN2Loss(Loss):
         if g_main:  # maximise the logits of generated images: -log sigmoid(D(G(z)))
             gen_img, _ = self.run_G(gen_z, gen_c, gen_h, sync=(sync and not g_pl))
             loss = softplus(-self.run_D(gen_img, gen_c, gen_h, sync=False))
+            self.stats["Loss/G/loss"] = loss.detach().mean()
             loss.mean().mul(gain).backward()
 
         if g_pl:  # path length: |J_w^T y| should stay near its running mean
@@ -89,6 +92,7 @@ class StyleGAN2Loss(Loss):
         if d_main:  # minimise the logits of generated images: -log(1 - sigmoid(D(G(z))))
             gen_img, _ = self.run_G(gen_z, gen_c, gen_h, sync=False)
             loss_gen = softplus(self.run_D(gen_img, gen_c, gen_h, sync=False))
+            self.stats["Loss/D/loss_gen"] = loss_gen.detach().mean()
             loss_gen.mean().mul(gain).backward()
 
         if d_main or d_r1:  # real images: logistic loss and/or R1 gradient penalty

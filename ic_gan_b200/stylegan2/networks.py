@@ -19,7 +19,7 @@ import math
 import torch
 from torch import nn
 
-from .modconv import modulated_conv2d
+from .modconv import modulated_conv2d, modulated_conv2d_act  # noqa: F401  (modulated_conv2d: reference name)
 from .ops import bias_act, conv2d_resample, upfirdn2d
 
 LOW_PRECISION = torch.bfloat16  # what the reference's `use_fp16` blocks compute in here
@@ -35,7 +35,11 @@ def _filter_buffer(module, taps):
 
 
 def _cast(x, dtype, channels_last):
-    return x.to(dtype=dtype, memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    """dtype cast; 4-D activations are ALWAYS channels-last on B200 (every kernel underneath is NHWC, so the reference's
+    `fp16_channels_last` switch has nothing left to choose -- it is accepted and ignored)."""
+    if x.ndim == 4:
+        return x.to(dtype=dtype, memory_format=torch.channels_last)
+    return x.to(dtype=dtype)
 
 
 class FullyConnectedLayer(nn.Module):
@@ -166,10 +170,12 @@ class SynthesisLayer(nn.Module):
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
         elif self.use_noise and noise_mode == "const":
             noise = self.noise_const * self.noise_strength
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+        # x*styles -> conv -> one pass of (*dcoefs + noise + bias -> act -> gain -> clamp)   (networks.py:77-95, :441-444)
+        return modulated_conv2d_act(x=x, weight=self.weight, styles=styles, noise=noise, bias=self.bias,
+                                    act=self.activation, gain=self.act_gain * gain, clamp=clamp, up=self.up,
+                                    padding=self.padding, resample_filter=self.resample_filter,
+                                    flip_weight=(self.up == 1))
 
 
 class ToRGBLayer(nn.Module):
@@ -184,8 +190,8 @@ class ToRGBLayer(nn.Module):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
-        return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
+        return modulated_conv2d_act(x=x, weight=self.weight, styles=styles, bias=self.bias, clamp=self.conv_clamp,
+                                    demodulate=False)
 
 
 class SynthesisBlock(nn.Module):

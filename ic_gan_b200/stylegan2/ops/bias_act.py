@@ -27,7 +27,29 @@ activation_funcs = {
 }
 
 
+def _fast_nhwc(x, b, yref, grad, dim, spec, alpha, gain, clamp):
+    """Channels-last 4-D tensors with lrelu / linear (everything the training path issues): the vectorised kernel
+    (8 elements per thread, no per-element div/mod).  Returns None when the call is not eligible."""
+    if not (x.ndim == 4 and dim == 1 and spec.cuda_idx in (1, 3) and grad in (0, 1) and x.shape[1] % 8 == 0
+            and x.shape[1] > 1 and x.dtype in (torch.float32, torch.bfloat16)
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        return None
+    if grad == 1 and yref is None and not (spec.cuda_idx == 1 and clamp < 0):
+        return None
+    N, C, H, W = x.shape
+    y = torch.empty_like(x)  # preserves channels-last
+    bb = None if (b is None or grad == 1) else b.float().contiguous()
+    yr = None if yref is None else yref.to(x.dtype).contiguous(memory_format=torch.channels_last)
+    call("icgan_bias_act_nhwc", ptr(x), ptr(yr), ptr(y), ptr(bb), None, None, None, 0, N, H * W, C, grad, spec.cuda_idx,
+         float(alpha), float(gain), float(clamp), dt(x), stream_ptr())
+    return y
+
+
 def _launch(x, b, xref, yref, dy, grad, dim, spec, alpha, gain, clamp):
+    if dy is None:
+        fast = _fast_nhwc(x, b, yref, grad, dim, spec, alpha, gain, clamp)
+        if fast is not None:
+            return fast
     x = x.contiguous(memory_format=torch.channels_last) if (x.ndim == 4 and x.stride(1) == 1 and x.shape[1] > 1) \
         else x.contiguous()
     y = torch.empty_like(x)
@@ -49,16 +71,17 @@ def _launch(x, b, xref, yref, dy, grad, dim, spec, alpha, gain, clamp):
     return y
 
 
-def bias_act(x, b=None, dim=1, act="linear", alpha=None, gain=None, clamp=None, impl="cuda"):
-    assert isinstance(x, torch.Tensor)
-    if impl != "cuda":
-        raise NotImplementedError("ic_gan_b200 has no PyTorch/CPU fallback for bias_act (impl='ref' lives in oracle/)")
+_fn_cache = {}
+
+
+def _function(dim, act, alpha, gain, clamp):
+    """The autograd Function of one (dim, act, alpha, gain, clamp) configuration, built once (a training step issues the
+    same handful of configurations thousands of times)."""
+    key = (dim, act, alpha, gain, clamp)
+    if key in _fn_cache:
+        return _fn_cache[key]
     spec = activation_funcs[act]
-    alpha = float(alpha if alpha is not None else spec.def_alpha)
-    gain = float(gain if gain is not None else spec.def_gain)
-    clamp = float(clamp if clamp is not None else -1)
-    if b is not None:
-        assert isinstance(b, torch.Tensor) and b.ndim == 1 and 0 <= dim < x.ndim and b.shape[0] == x.shape[dim]
+    needs_x = "x" in spec.ref or spec.has_2nd_grad
 
     class BiasActCuda(torch.autograd.Function):
         @staticmethod
@@ -66,11 +89,10 @@ def bias_act(x, b=None, dim=1, act="linear", alpha=None, gain=None, clamp=None, 
             y = x
             if act != "linear" or gain != 1 or clamp >= 0 or b is not None:
                 y = _launch(x, b, None, None, None, 0, dim, spec, alpha, gain, clamp)
-            ctx.save_for_backward(x if "x" in spec.ref or spec.has_2nd_grad else None,
-                                  b if "x" in spec.ref or spec.has_2nd_grad else None,
-                                  # the reference's CUDA path does not save y for act='linear' and therefore ignores the
-                                  # clamp in backward (bias_act.py:236-241); its own impl='ref' (the pinned oracle) masks
-                                  # it, which is the mathematically correct derivative -- followed here.
+            # The reference's CUDA path does not save y for act='linear' and therefore ignores the clamp in backward
+            # (bias_act.py:236-241); its own impl='ref' (the pinned oracle) masks it, which is the mathematically
+            # correct derivative -- followed here.
+            ctx.save_for_backward(x if needs_x else None, b if needs_x else None,
                                   y if ("y" in spec.ref or clamp >= 0) else None)
             ctx.has_b = b is not None
             return y
@@ -106,4 +128,19 @@ def bias_act(x, b=None, dim=1, act="linear", alpha=None, gain=None, clamp=None, 
                 d_b = d_x.sum([i for i in range(d_x.ndim) if i != dim])
             return d_dy, d_x, d_b, None
 
-    return BiasActCuda.apply(x, b)
+    _fn_cache[key] = BiasActCuda
+    return BiasActCuda
+
+
+def bias_act(x, b=None, dim=1, act="linear", alpha=None, gain=None, clamp=None, impl="cuda"):
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("bias_act: x must be a tensor")
+    if impl != "cuda":
+        raise NotImplementedError("ic_gan_b200 has no PyTorch/CPU fallback for bias_act (impl='ref' lives in oracle/)")
+    spec = activation_funcs[act]
+    alpha = float(alpha if alpha is not None else spec.def_alpha)
+    gain = float(gain if gain is not None else spec.def_gain)
+    clamp = float(clamp if clamp is not None else -1)
+    if b is not None and not (isinstance(b, torch.Tensor) and b.ndim == 1 and 0 <= dim < x.ndim and b.shape[0] == x.shape[dim]):
+        raise ValueError("bias_act: b must be a vector matching x.shape[dim]")
+    return _function(dim, act, alpha, gain, clamp).apply(x, b)

@@ -1,68 +1,80 @@
-"""Drop-in for ``stylegan2_ada_pytorch/torch_utils/ops/conv2d_resample.py`` (``conv2d_resample`` :79-216): 2-D convolution
-with optional up/down-sampling, choosing between strided conv, transposed conv and FIR resampling exactly as the
-reference does, on top of this package's ``conv2d_gradfix`` and ``upfirdn2d``."""
+"""Drop-in for ``stylegan2_ada_pytorch/torch_utils/ops/conv2d_resample.py`` (``conv2d_resample`` :79-216): convolution
+with optional FIR up/down-sampling.
+
+The function is  y = decimate_down( FIR_f( conv_w( pad( FIR_f*up^2( zero_stuff_up(x) ) ) ) ) )  and is always evaluated
+as the cheapest equivalent chain of the two primitives this package runs natively -- ``upfirdn2d`` (shared-memory-tiled
+NHWC kernel) and ``conv2d_gradfix`` (tcgen05 implicit GEMM, including stride 2 and the stride-2 transposed form).  The
+chain is picked by :func:`plan`; it reproduces the evaluation order of the reference (which FIR runs before or after
+which convolution decides the rounding, so parity needs the same order)."""
 from __future__ import annotations
+
+from typing import List, Tuple
 
 import torch
 
 from . import conv2d_gradfix, upfirdn2d
-from .upfirdn2d import _get_filter_size, _parse_padding
+
+Step = Tuple  # ("fir", dict of upfirdn2d kwargs) | ("conv", dict(stride, padding, transpose))
 
 
-def _conv(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True):
-    if not flip_weight:  # conv2d computes correlation; a true convolution needs the taps flipped
-        w = w.flip([2, 3])
-    op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
-    return op(x, w, stride=stride, padding=padding, groups=groups)
+def plan(kh: int, kw: int, fh: int, fw: int, up: int, down: int, padding) -> List[Step]:
+    """Chain of primitive steps for one geometry (pure arithmetic, unit-tested on its own)."""
+    left, right, top, bottom = upfirdn2d._pad4(padding)
+    if up > 1:      # keep the image centred under the interpolation filter
+        left, right = left + (fw + up - 1) // 2, right + (fw - up) // 2
+        top, bottom = top + (fh + up - 1) // 2, bottom + (fh - up) // 2
+    if down > 1:    # ... and under the anti-aliasing filter
+        left, right = left + (fw - down + 1) // 2, right + (fw - down) // 2
+        top, bottom = top + (fh - down + 1) // 2, bottom + (fh - down) // 2
+    frame = [left, right, top, bottom]
+    pointwise = kh == 1 and kw == 1
+
+    if pointwise and up == 1 and down > 1:       # decimate first: the 1x1 convolution then sees down^2 fewer pixels
+        return [("fir", dict(down=down, padding=frame)), ("conv", dict())]
+    if pointwise and down == 1 and up > 1:       # 1x1 at low resolution, interpolate afterwards
+        return [("conv", dict()), ("fir", dict(up=up, padding=frame, gain=up ** 2))]
+    if up == 1 and down > 1:                     # low-pass at full resolution, stride-`down` convolution
+        return [("fir", dict(padding=frame)), ("conv", dict(stride=down))]
+    if up > 1:                                   # stride-`up` transposed convolution, then the interpolation filter
+        # the transposed convolution already spreads each sample over a kh x kw footprint: take that out of the frame
+        left, right = left - (kw - 1), right - (kw - up)
+        top, bottom = top - (kh - 1), bottom - (kh - up)
+        crop_x, crop_y = max(min(-left, -right), 0), max(min(-top, -bottom), 0)
+        steps = [("conv", dict(stride=up, padding=[crop_y, crop_x], transpose=True)),
+                 ("fir", dict(padding=[left + crop_x, right + crop_x, top + crop_y, bottom + crop_y], gain=up ** 2))]
+        if down > 1:
+            steps.append(("fir", dict(down=down)))
+        return steps
+    if left == right and top == bottom and left >= 0 and top >= 0:   # nothing to resample
+        return [("conv", dict(padding=[top, left]))]
+    steps = [("fir", dict(up=up, padding=frame, gain=up ** 2, no_filter=(up == 1))), ("conv", dict())]
+    if down > 1:
+        steps.append(("fir", dict(down=down)))
+    return steps
 
 
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
-    assert isinstance(x, torch.Tensor) and x.ndim == 4 and isinstance(w, torch.Tensor) and w.ndim == 4
-    assert isinstance(up, int) and up >= 1 and isinstance(down, int) and down >= 1 and groups >= 1
-    co, ci_g, kh, kw = (int(s) for s in w.shape)
-    fw, fh = _get_filter_size(f)
-    px0, px1, py0, py1 = _parse_padding(padding)
-    if up > 1:  # FIR padding that keeps the image aligned after zero-insertion
-        px0 += (fw + up - 1) // 2
-        px1 += (fw - up) // 2
-        py0 += (fh + up - 1) // 2
-        py1 += (fh - up) // 2
-    if down > 1:
-        px0 += (fw - down + 1) // 2
-        px1 += (fw - down) // 2
-        py0 += (fh - down + 1) // 2
-        py1 += (fh - down) // 2
-    pad4 = [px0, px1, py0, py1]
-
-    if kw == 1 and kh == 1 and down > 1 and up == 1:  # 1x1 + downsample: filter/decimate first
-        x = upfirdn2d.upfirdn2d(x, f, down=down, padding=pad4, flip_filter=flip_filter)
-        return _conv(x, w, groups=groups, flip_weight=flip_weight)
-    if kw == 1 and kh == 1 and up > 1 and down == 1:  # 1x1 + upsample: convolve at low resolution first
-        x = _conv(x, w, groups=groups, flip_weight=flip_weight)
-        return upfirdn2d.upfirdn2d(x, f, up=up, padding=pad4, gain=up ** 2, flip_filter=flip_filter)
-    if down > 1 and up == 1:  # low-pass, then strided convolution
-        x = upfirdn2d.upfirdn2d(x, f, padding=pad4, flip_filter=flip_filter)
-        return _conv(x, w, stride=down, groups=groups, flip_weight=flip_weight)
-    if up > 1:  # transposed (stride = up) convolution, then low-pass
-        if groups == 1:
-            wt = w.transpose(0, 1)
-        else:
-            wt = w.reshape(groups, co // groups, ci_g, kh, kw).transpose(1, 2).reshape(groups * ci_g, co // groups, kh, kw)
-        px0 -= kw - 1
-        px1 -= kw - up
-        py0 -= kh - 1
-        py1 -= kh - up
-        pxt, pyt = max(min(-px0, -px1), 0), max(min(-py0, -py1), 0)
-        x = _conv(x, wt, stride=up, padding=[pyt, pxt], groups=groups, transpose=True, flip_weight=(not flip_weight))
-        x = upfirdn2d.upfirdn2d(x, f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2,
-                                flip_filter=flip_filter)
-        if down > 1:
-            x = upfirdn2d.upfirdn2d(x, f, down=down, flip_filter=flip_filter)
-        return x
-    if px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:  # plain convolution
-        return _conv(x, w, padding=[py0, px0], groups=groups, flip_weight=flip_weight)
-    x = upfirdn2d.upfirdn2d(x, (f if up > 1 else None), up=up, padding=pad4, gain=up ** 2, flip_filter=flip_filter)
-    x = _conv(x, w, groups=groups, flip_weight=flip_weight)
-    if down > 1:
-        x = upfirdn2d.upfirdn2d(x, f, down=down, flip_filter=flip_filter)
+    if not (isinstance(x, torch.Tensor) and x.ndim == 4 and isinstance(w, torch.Tensor) and w.ndim == 4):
+        raise ValueError("conv2d_resample: x and w must be 4-D tensors")
+    if not (isinstance(up, int) and up >= 1 and isinstance(down, int) and down >= 1 and groups >= 1):
+        raise ValueError("conv2d_resample: up, down, groups must be positive integers")
+    co, ci_g, kh, kw = (int(v) for v in w.shape)
+    fw, fh = upfirdn2d._taps(f)
+    for kind, kw_args in plan(kh, kw, fh, fw, up, down, padding):
+        if kind == "fir":
+            args = dict(kw_args)
+            filt = None if args.pop("no_filter", False) else f
+            x = upfirdn2d.upfirdn2d(x, filt, flip_filter=flip_filter, **args)
+            continue
+        transpose = kw_args.get("transpose", False)
+        weight = w
+        if transpose:  # [Co, Ci/g, kh, kw] -> the [Ci, Co/g, kh, kw] layout of a transposed convolution
+            weight = (w.transpose(0, 1) if groups == 1 else
+                      w.reshape(groups, co // groups, ci_g, kh, kw).transpose(1, 2).reshape(groups * ci_g, co // groups, kh, kw))
+        # conv2d computes a correlation; a true convolution (flip_weight=False) reverses the taps -- and a transposed
+        # convolution reverses them once more
+        if flip_weight == transpose:
+            weight = weight.flip([2, 3])
+        op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
+        x = op(x, weight, stride=kw_args.get("stride", 1), padding=kw_args.get("padding", 0), groups=groups)
     return x

@@ -68,6 +68,28 @@ int icgan_conv2d_rgb_tc(const void* x, const void* wcol, const float* alpha_dev,
 int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, int B, int H, int W, int Cin, int Cout,
                           int ksize, void* stream);
 
+/* Generalised tensor-core convolution: an explicit tap list instead of a k x k window, optional input stride 2 and an
+ * affine output-pixel mapping -- what the strided and transposed convolutions of StyleGAN2's conv2d_resample need
+ * (stylegan2_ada_pytorch/torch_utils/ops/conv2d_resample.py:152-195 -> conv2d_gradfix.conv2d(stride=2) /
+ * conv_transpose2d(stride=2), i.e. cudnn_convolution / cudnn_convolution_transpose) without zero-insertion:
+ *   for (h, w) in the Hd x Wd tile domain:
+ *     y[n, h*osy+ooy, w*osx+oox, co] = sum_t sum_ci x[n, h*in_stride+tap_dh[t], w*in_stride+tap_dw[t], ci] * wk[co, tap_w[t], ci]
+ *                                      + bias[co] + residual[n, h*osy+ooy, w*osx+oox, co]
+ * x: [B,H,W,Cin] bf16 (reads outside the tensor are zero), wk: [Cout, wtaps, Cin] bf16, y/residual: [B,OH,OW,Cout];
+ * tap_* are HOST int arrays of ntaps (<= 16) entries. A stride-2 convolution is one call (in_stride=2); a stride-2
+ * transposed convolution is four calls, one per output parity class (osy=osx=2, oo* = parity), each with the 1, 2 or 4
+ * taps that reach that class. */
+int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* bias, const void* residual, void* y, int B, int H,
+                       int W, int Cin, int Cout, int wtaps, int ntaps, const int* tap_dh_host, const int* tap_dw_host,
+                       const int* tap_w_host, int in_stride, int Hd, int Wd, int OH, int OW, int osy, int ooy, int osx,
+                       int oox, int out_dtype, int res_dtype, void* stream);
+/* Weight gradient of the same family (replaces cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight,
+ * conv2d_gradfix.py:223-227):  out[ca, t, cb] += sum_{n,h,w} a[n,h,w,ca] * b[n, h*in_stride+tap_dh[t], w*in_stride+tap_dw[t], cb]
+ * a: [B,Ha,Wa,Ca] bf16, b: [B,Hb,Wb,Cb] bf16 (zero outside), out: float32 [Ca, ntaps, Cb], ACCUMULATED. Cb%16==0, Ca%8==0. */
+int icgan_conv2d_wgrad_tc_ex(const void* a, const void* b, float* out, int B, int Ha, int Wa, int Ca, int Hb, int Wb,
+                             int Cb, int ntaps, const int* tap_dh_host, const int* tap_dw_host, int in_stride,
+                             void* stream);
+
 /* Generic CUDA-core path (float32 accumulate; any channel counts, e.g. Cin=3 / Cout=3; any stride/pad).
  * H, W are INPUT dims; output is [(H+2*pad-k)/stride+1, ...]. x/y dtype per in_dtype/out_dtype; wk float32
  * [Cout,k,k,Cin]. Same epilogue as icgan_conv2d_tc. */
@@ -224,6 +246,31 @@ int icgan_bias_act(const void* x, const void* b, const void* xref, const void* y
 int icgan_upfirdn2d(const void* x, const float* f, void* y, int N, int C, int inH, int inW, int fh, int fw, int upx,
                     int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                     int channels_last, int dtype, void* stream);
+
+/* Channels-last (NHWC) fast paths of the two ops above plus the elementwise pieces of modulated_conv2d
+ * (stylegan2_ada_pytorch/training/networks.py:77-95: x*styles -> conv -> *dcoefs + noise -> bias_act), HBM-bound, one
+ * pass each.  Epilogue inputs are float32: pre_scale [N,C] (demodulation coefficients), noise [N or 1, outH, outW],
+ * noise_strength (device scalar, NULL = 1), bias [C], s2 [N,C] (styles of the NEXT layer; y2 = y*s2 is its modulated
+ * input). act: 0 = no epilogue, 1 = linear, 3 = lrelu (bias_act.py:26-99 ids); clamp < 0 disables clamping. */
+/* Shared-memory-tiled upfirdn2d (upfirdn2d.cu:100-203 `upfirdn2d_kernel_small` re-designed for NHWC), 4x4 filter,
+ * (up, down) in {(1,1), (2,1), (1,2)}:  y = epilogue(gain * upfirdn(x)); x [N,inH,inW,C], y [N,outH,outW,C]. */
+int icgan_upfirdn2d_nhwc(const void* x, const float* f4x4, void* y, int N, int C, int inH, int inW, int up, int down,
+                         int padx0, int padx1, int pady0, int pady1, int flip, float gain, const float* pre_scale,
+                         const float* noise, const float* noise_strength, int noise_per_sample, const float* bias,
+                         int act, float alpha, float act_gain, float clamp, const float* s2, void* y2, int dtype,
+                         void* stream);
+/* y[n,p,c] = x[n,p,c] * s[n,c]  (networks.py:78 `x * styles`), optional float32 <-> bfloat16 cast. C % 8 == 0. */
+int icgan_modulate(const void* x, const float* s, void* y, int N, int64_t hw, int C, int in_dtype, int out_dtype,
+                   void* stream);
+/* out[n,c] = sum_p a[n,p,c]*b[n,p,c]  (the adjoint of icgan_modulate: gradients w.r.t. styles / dcoefs). out float32 [N,C]. */
+int icgan_chan_dot(const void* a, const void* b, float* out, int N, int64_t hw, int C, int a_dtype, int b_dtype,
+                   void* stream);
+/* bias_act for NHWC tensors, 8 elements per thread (bias_act.cu:26-150 for act 1/3, grad 0/1):
+ *   grad 0: y = clamp(act(x*pre_scale[n,c] + noise[n,p]*noise_strength + bias[c]) * gain)
+ *   grad 1: y = x * gain * act'(yref) * [|yref| < clamp] * pre_scale[n,c]       (x = incoming gradient) */
+int icgan_bias_act_nhwc(const void* x, const void* yref, void* y, const float* bias, const float* pre_scale,
+                        const float* noise, const float* noise_strength, int noise_per_sample, int N, int64_t hw, int C,
+                        int grad, int act, float alpha, float gain, float clamp, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimiser step fused with the EMA of the generator.

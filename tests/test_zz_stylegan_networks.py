@@ -18,6 +18,7 @@ from ic_gan_b200.stylegan2 import loss as b200_loss
 from ic_gan_b200.stylegan2 import networks as N
 from ic_gan_b200.stylegan2.ops import bias_act as m_bias_act
 from ic_gan_b200.stylegan2.ops import conv2d_gradfix as m_gradfix
+from ic_gan_b200.stylegan2.ops import elementwise as m_elem
 from ic_gan_b200.stylegan2.ops import fma as m_fma
 from ic_gan_b200.stylegan2.ops import upfirdn2d as m_upfirdn2d
 from oracle import stylegan_nets_oracle as O
@@ -60,6 +61,16 @@ def cpu_ops(monkeypatch):
     monkeypatch.setattr(m_gradfix, "conv2d", F.conv2d)
     monkeypatch.setattr(m_gradfix, "conv_transpose2d", F.conv_transpose2d)
     monkeypatch.setattr(m_fma, "fma", lambda a, b, c: a * b + c)
+    monkeypatch.setattr(m_elem, "modulate", lambda x, s, out_dtype=None: x * s.to(x.dtype).reshape(x.shape[0], -1, 1, 1))
+    monkeypatch.setattr(m_elem, "chan_dot", lambda a, b: (a * b).sum([2, 3]))
+
+    def mod_bias_act(x, pre=None, noise=None, bias=None, act="linear", alpha=0.2, gain=1.0, clamp=None):
+        if pre is not None:
+            x = x * pre.to(x.dtype).reshape(x.shape[0], -1, 1, 1)
+        if noise is not None:
+            x = x + noise.to(x.dtype).reshape(-1, 1, x.shape[2], x.shape[3])
+        return oops.bias_act(x, None if bias is None else bias.to(x.dtype), dim=1, act=act, alpha=None, gain=gain, clamp=clamp)
+    monkeypatch.setattr(m_elem, "mod_bias_act", mod_bias_act)
 
 
 def _close(got, ref, what, tol=2e-5):
@@ -243,3 +254,49 @@ def _phase_vs_oracle(cuda_device, phase, gain, tol):
     print(f"{phase}: worst gradient rel-L2 vs CPU oracle: " + ", ".join(f"{k} {r:.2e}" for r, k in report[:4]))
     bad = [(r, k) for r, k in report if r > tol]
     assert not bad, f"{phase}: {bad[:6]}"
+
+
+# ------------------------------------------------------------------------------------------------------- emulated kernels
+@pytest.fixture
+def emu(monkeypatch):
+    """The REAL op stack of the package (autograd Functions, tap tables, layouts, split-bf16 sequencing) over a CPU
+    emulation of the C ABI (tests/kernel_emulator.py): exercises everything above the kernels without a GPU."""
+    from tests.kernel_emulator import emulated
+    with emulated(monkeypatch):
+        yield
+
+
+def test_modules_on_emulated_kernels(emu):
+    meta, fx, _ = _load()
+    G, D = _build(meta)
+    z, h, x = inputs()
+    G.eval(); D.eval()
+    with torch.no_grad():
+        _close(G(z, None, h, noise_mode="const"), fx["img_const"], "img_const", tol=3e-4)
+        _close(G(z, None, h, noise_mode="none"), fx["img_none"], "img_none", tol=3e-4)
+        _close(D(x, None, h), fx["d_real"], "d_real", tol=3e-4)
+    G.train(); D.train()
+    img = G(z, None, h, noise_mode="const")
+    _close(img, fx["img_train"], "img_train", tol=3e-4)
+    F.softplus(-D(img, None, h)).mean().backward()
+    params = dict(G.named_parameters())
+    for k in meta["grad_keys_g"]:
+        ref = fx["G_grad/" + k]
+        rel = np.linalg.norm(params[k].grad.numpy() - ref) / max(np.linalg.norm(ref), 1e-30)
+        assert rel <= 2e-3, f"G grad {k}: {rel:.3e}"
+
+
+def test_bf16_blocks_on_emulated_kernels(emu):
+    meta, fx, _ = _load()
+    G, D = _build(meta, num_fp16_res=2)
+    z, h, x = inputs()
+    G.eval(); D.eval()
+    with torch.no_grad():
+        _close(G(z, None, h, noise_mode="const"), fx["img_const"], "img_const bf16", tol=8e-2)
+        _close(D(x, None, h), fx["d_real"], "d_real bf16", tol=5e-2)
+
+
+@pytest.mark.parametrize("phase,gain", [("Gmain", 1.0), ("Greg", 4.0), ("Dmain", 1.0), ("Dreg", 16.0)])
+def test_loss_phases_on_emulated_kernels(emu, phase, gain):
+    """All four phases -- both double backwards included -- through the package's own Functions."""
+    _phase_vs_oracle(torch.device("cpu"), phase, gain, 5e-3)
