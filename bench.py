@@ -39,6 +39,30 @@ METRIC = "images/sec G+D step, IC-GAN BigGAN"
 JSON_OUT = [None]  # where the one JSON line goes (the original stdout when fd 1 has been pointed at stderr)
 
 
+T0 = time.perf_counter()
+
+
+def note(msg):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    print(f"[bench {time.perf_counter() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def cpu_leg(flag, timeout_s=240):
+    """Run `bench.py <flag>` (a CPU baseline leg) in a subprocess with bounded threads and wall time; returns its JSON
+    or None.  A CPU leg that overruns must never take the GPU numbers down with it."""
+    threads = min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__)] + flag, env=env, capture_output=True, text=True,
+                             timeout=timeout_s)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # timeout, crash, no output
+        note(f"cpu leg {flag} unavailable: {type(e).__name__}")
+        return None
+
+
 def emit(line):
     out = JSON_OUT[0] or sys.stdout
     print(json.dumps(line), file=out, flush=True)
@@ -435,12 +459,19 @@ def run_sg256(args):
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     metric = "images/sec G+D iteration, IC-GAN StyleGAN2-ADA 256x256"
+    if args.sg_cpu_worker:
+        torch.set_num_threads(int(os.environ.get("OMP_NUM_THREADS", "16")))
+        ips, it, times = sg_cpu_rate(2)
+        print(json.dumps({"ips": ips, "it": it, "times": times, "threads": torch.get_num_threads()}), flush=True)
+        return
     if args.impl == "reference":
         if rank:
             return
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-        torch.set_num_threads(cores)
-        ips, it, times = sg_cpu_rate(2)
+        res = cpu_leg(["--workload", "sg256", "--sg-cpu-worker"], 400)
+        if res is None:
+            emit({"impl": "reference", "unavailable": "oracle StyleGAN2 iteration did not finish within 400 s on this host"})
+            return
+        ips, it, times, cores = res["ips"], res["it"], res["times"], res["threads"]
         sample = ("oracle iteration (CPU restatement of training/loss.py:85-194 over training/networks.py), fp32, batch 2: "
                   + ", ".join(f"{k} {v:.1f} s" for k, v in times.items()) + f"; iteration = Gmain + Dmain + Greg/4 + Dreg/16 = {it:.1f} s")
         emit({"impl": "reference", "metric": metric, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -522,8 +553,11 @@ def run_sg256(args):
 
     if args.ncu:
         args.no_e2e = args.no_cpu_baseline = True
+    note("sg256: networks built, warm-up")
     for i in range(args.warmup if args.ncu else max(args.warmup, 3)):
         iteration(real_dev, h_dev)
+        torch.cuda.synchronize()
+        note(f"sg256: warm-up iteration {i} done")
     it_count[0] = 0
     barrier()
     sampler = ClockSampler(local)
@@ -543,6 +577,7 @@ def run_sg256(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    note(f"sg256: {ms:.1f} ms per iteration (device-resident inputs)")
     clocks = sampler.stop() if rank == 0 else None
     e2e = None
     if not args.no_e2e:
@@ -601,11 +636,11 @@ def run_sg256(args):
             "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-        torch.set_num_threads(cores)
-        ips, it, times = sg_cpu_rate(2)
-        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": "oracle iteration at batch 2 (Gmain + Dmain + Greg/4 + Dreg/16 = %.1f s)" % it}
+        note("cpu baseline leg")
+        res = cpu_leg(["--workload", "sg256", "--sg-cpu-worker"], 240)
+        if res is not None:
+            line["cpu_baseline"] = {"value": res["ips"], "unit": "images/s", "cores": res["threads"], "kind": "port",
+                                    "sample": "oracle iteration at batch 2 (Gmain + Dmain + Greg/4 + Dreg/16 = %.1f s)" % res["it"]}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -629,6 +664,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--threads", type=int, default=ORACLE_THREADS, help=argparse.SUPPRESS)
     ap.add_argument("--affinity", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--sg-cpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: short warm-up allowed, no e2e/cpu legs "
                                                        "(a number printed by such a run is never a bench value)")
     args = ap.parse_args()

@@ -75,6 +75,7 @@ SIGNATURES = {
     "icgan_modulate": [vp, fp, vp, i32, i64, i32, i32, i32, vp],
     "icgan_chan_dot": [vp, vp, fp, i32, i64, i32, i32, i32, vp],
     "icgan_bias_act_nhwc": [vp, vp, vp, fp, fp, fp, fp, i32, i32, i64, i32, i32, i32, f32, f32, f32, i32, vp],
+    "icgan_mod_bias_act_bwd": [vp, vp, vp, fp, vp, fp, fp, fp, i32, i64, i32, i32, f32, f32, f32, i32, vp],
     "icgan_adam_ema_step": [fp, fp, fp, fp, fp, i64, f64, f64, f64, f64, i64, f64, f64, vp],
     "icgan_ema_lerp": [fp, fp, i64, f64, vp],
     "icgan_gemm_tc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
@@ -108,7 +109,7 @@ def last_error() -> str:
 
 
 # kernels launched per entry point (everything else launches exactly one); bench.py reports the running total
-KERNELS_PER_CALL = {"icgan_bn_train_stats": 2, "icgan_sn_power_iteration": 5, "icgan_sn_weight_grad": 2, "icgan_knn_exact_row": 2}
+KERNELS_PER_CALL = {"icgan_mod_bias_act_bwd": 1, "icgan_bn_train_stats": 2, "icgan_sn_power_iteration": 5, "icgan_sn_weight_grad": 2, "icgan_knn_exact_row": 2}
 LAUNCHES = 0
 
 

@@ -309,6 +309,80 @@ bias_act_vec_kernel(const T* __restrict__ x, const T* __restrict__ yref, T* __re
   }
 }
 
+// First-order backward of y = clamp(act(x*pre[n,c] + noise[n,p] + bias[c]) * gain) in ONE pass:
+//   t = dy * gain * act'(y) * [|y| < clamp];  dx = t * pre;  dpre[n,c] += sum_p t*x;  dbias_n[n,c] += sum_p t;
+//   dnoise[n,p] = sum_c t
+// (the composed form is five passes: activation gradient, modulate, chan_dot and two reductions).
+// grid = (pixel slabs, N); 256 threads = (256/cv pixels) x (cv = C/8 channel vectors); needs 256 % cv == 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+mod_bias_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
+                        const float* __restrict__ pre, T* __restrict__ dx, float* __restrict__ dpre,
+                        float* __restrict__ dbias_n, float* __restrict__ dnoise, int64_t hw, int C, int slab, int act,
+                        float alpha, float gain, float clamp) {
+  const int cv = C / 8, pp = 256 / cv;
+  const int lc = threadIdx.x % cv, prow = threadIdx.x / cv;
+  const int n = blockIdx.y;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * slab, p1 = min(hw, p0 + slab);
+  const int c = lc * 8;
+  float pv[8], apre[8], ab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { pv[k] = pre ? pre[static_cast<int64_t>(n) * C + c + k] : 1.f; apre[k] = 0.f; ab[k] = 0.f; }
+  const int red_w = cv < 32 ? cv : 32;  // lanes of a warp that share a pixel
+  for (int64_t pb = p0; pb < p1; pb += pp) {  // uniform trip count: the shuffles below need every lane of the warp
+    const int64_t px = pb + prow;
+    const bool live = px < p1;
+    const int64_t o = (static_cast<int64_t>(n) * hw + (live ? px : p0)) * C + c;
+    float g[8], yr[8], xv[8];
+    Pack<T>::load(dy + o, g);
+    Pack<T>::load(y + o, yr);
+    if (x) Pack<T>::load(x + o, xv);
+    if (!live) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = 0.f;
+    }
+    float s = 0.f, d[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = g[k];
+      if (act == 3) t = yr[k] > 0.f ? t : t * alpha;
+      t *= gain;
+      if (clamp >= 0.f) t = (yr[k] > -clamp && yr[k] < clamp) ? t : 0.f;
+      s += t;
+      ab[k] += t;
+      if (x) apre[k] = fmaf(t, xv[k], apre[k]);
+      d[k] = t * pv[k];
+    }
+    if (live) Pack<T>::store(dx + o, d);
+    if (dnoise) {
+      for (int off = red_w >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (live && (threadIdx.x & (red_w - 1)) == 0) {
+        if (cv <= 32) dnoise[static_cast<int64_t>(n) * hw + px] = s;
+        else atomicAdd(dnoise + static_cast<int64_t>(n) * hw + px, s);
+      }
+    }
+  }
+  // reduce the per-thread channel sums over the pixel rows of the block
+  __shared__ float red[2][256 * 8 / 2 + 8];  // [which][ (prow, lc, k) ] folded: processed in two halves below
+  float* r0 = &red[0][0];
+  for (int which = 0; which < 2; ++which) {
+    float* acc = which == 0 ? apre : ab;
+    float* dst = which == 0 ? dpre : dbias_n;
+    if (!dst) continue;
+    // tree over prow using shared memory in 8-channel slices
+    for (int k = 0; k < 8; ++k) {
+      __syncthreads();
+      r0[threadIdx.x] = acc[k];
+      __syncthreads();
+      if (prow == 0) {
+        float t = 0.f;
+        for (int r = 0; r < pp; ++r) t += r0[r * cv + lc];
+        atomicAdd(dst + static_cast<int64_t>(n) * C + c + k, t);
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace icgan
 
@@ -406,6 +480,32 @@ extern "C" int icgan_chan_dot(const void* a, const void* b, float* out, int N, i
   else if (a_dtype == ICGAN_BF16 && b_dtype == ICGAN_F32) ICGAN_CD(__nv_bfloat16, float);
   else { icgan::set_error("icgan_chan_dot: dtypes must be float32 / bfloat16"); return -1; }
 #undef ICGAN_CD
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_mod_bias_act_bwd(const void* dy, const void* y, const void* x, const float* pre_scale, void* dx,
+                                      float* dpre, float* dbias_n, float* dnoise, int N, int64_t hw, int C, int act,
+                                      float alpha, float gain, float clamp, int dtype, void* stream) {
+  ICGAN_REQUIRE(dy && y && dx && N > 0 && hw > 0, "icgan_mod_bias_act_bwd: bad arguments");
+  ICGAN_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "icgan_mod_bias_act_bwd: C/8 must divide 256 (got C=%d)", C);
+  ICGAN_REQUIRE(act == 1 || act == 3, "icgan_mod_bias_act_bwd: linear / lrelu only");
+  ICGAN_REQUIRE(!dpre || x, "icgan_mod_bias_act_bwd: dpre needs x");
+  if (dpre) ICGAN_CUDA(cudaMemsetAsync(dpre, 0, static_cast<size_t>(N) * C * 4, STREAM));
+  if (dbias_n) ICGAN_CUDA(cudaMemsetAsync(dbias_n, 0, static_cast<size_t>(N) * C * 4, STREAM));
+  if (dnoise && C / 8 > 32) ICGAN_CUDA(cudaMemsetAsync(dnoise, 0, static_cast<size_t>(N) * hw * 4, STREAM));
+  const int pp = 256 / (C / 8);
+  int slabs = static_cast<int>((static_cast<int64_t>(num_sms()) * 6 + N - 1) / N);
+  const int64_t max_slabs = (hw + pp - 1) / pp;
+  if (slabs > max_slabs) slabs = static_cast<int>(max_slabs);
+  if (slabs < 1) slabs = 1;
+  int slab = static_cast<int>((hw + slabs - 1) / slabs);
+  slab = (slab + pp - 1) / pp * pp;
+  dim3 grid(static_cast<unsigned>((hw + slab - 1) / slab), static_cast<unsigned>(N));
+#define ICGAN_MB(T) mod_bias_act_bwd_kernel<T><<<grid, 256, 0, STREAM>>>(static_cast<const T*>(dy), static_cast<const T*>(y), static_cast<const T*>(x), pre_scale, static_cast<T*>(dx), dpre, dbias_n, dnoise, hw, C, slab, act, alpha, gain, clamp)
+  if (dtype == ICGAN_BF16) ICGAN_MB(__nv_bfloat16);
+  else { icgan::set_error("icgan_mod_bias_act_bwd: bfloat16 activations only"); return -1; }
+#undef ICGAN_MB
   ICGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from .modconv import modulated_conv2d, modulated_conv2d_act  # noqa: F401  (modulated_conv2d: reference name)
-from .ops import bias_act, conv2d_resample, upfirdn2d
+from .ops import bias_act, conv2d_resample, elementwise, upfirdn2d
 
 LOW_PRECISION = torch.bfloat16  # what the reference's `use_fp16` blocks compute in here
 _SQRT_HALF = math.sqrt(0.5)
@@ -91,7 +91,8 @@ class Conv2dLayer(nn.Module):
         x = conv2d_resample.conv2d_resample(x=x, w=w, f=self.resample_filter, up=self.up, down=self.down,
                                             padding=self.padding, flip_weight=(self.up == 1))
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+        # bias + activation + gain + clamp in one pass, and ONE pass again for (dx, dbias) in the first-order backward
+        return elementwise.mod_bias_act(x, bias=b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
 
 
 class MappingNetwork(nn.Module):

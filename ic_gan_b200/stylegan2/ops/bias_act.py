@@ -106,7 +106,7 @@ def _function(dim, act, alpha, gain, clamp):
                 if act != "linear" or gain != 1 or clamp >= 0:
                     dx = BiasActCudaGrad.apply(dy, x, b, y)
             if ctx.needs_input_grad[1] and ctx.has_b:
-                db = dx.sum([i for i in range(dx.ndim) if i != dim])
+                db = dx.sum([i for i in range(dx.ndim) if i != dim], dtype=torch.float32).to(dx.dtype)
             return dx, db
 
     class BiasActCudaGrad(torch.autograd.Function):

@@ -269,7 +269,7 @@ def _op(transpose, weight_shape, stride, padding, output_padding, groups):
             if ctx.needs_input_grad[1] and not weight_gradients_disabled:
                 dw = Conv2dGradWeight.apply(dy, x)
             if ctx.needs_input_grad[2] and ctx.has_b:
-                db = dy.float().sum([0, 2, 3]).to(dy.dtype)
+                db = dy.sum([0, 2, 3], dtype=torch.float32).to(dy.dtype)
             return dx, dw, db
 
     class Conv2dGradWeight(torch.autograd.Function):

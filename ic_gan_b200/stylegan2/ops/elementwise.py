@@ -88,7 +88,7 @@ class _ActGradFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dy, y, act_id, alpha, gain, clamp):
         dy = _cl(dy)
-        if dy.dtype != y.dtype:
+        if y is not None and dy.dtype != y.dtype:
             dy = dy.to(y.dtype)
         N, C, H, W = dy.shape
         t = torch.empty_like(dy)
@@ -118,7 +118,11 @@ class ModBiasActFn(torch.autograd.Function):
         call("icgan_bias_act_nhwc", ptr(xc), None, ptr(y), ptr(b), ptr(pre_c), ptr(nz), None,
              int(nz is not None and nz.shape[0] > 1), N, H * W, C, 0, act_id, float(alpha), float(gain), float(clamp),
              dt(xc), stream_ptr())
-        ctx.save_for_backward(x, pre, y)  # inputs (and the output) themselves, so second derivatives reach their history
+        # inputs (and the output) themselves, so second derivatives reach their history; a linear, unclamped epilogue needs
+        # no y in its backward, which keeps the caller free to update y in place (`y.add_(x)` of the residual blocks)
+        needs_y = act_id != 1 or clamp >= 0
+        ctx.save_for_backward(x, pre, y if needs_y else None)
+        ctx.shape, ctx.out_dtype = tuple(y.shape), y.dtype
         ctx.cfg = (act_id, alpha, gain, clamp)
         ctx.noise_shape = None if noise is None else tuple(noise.shape)
         ctx.noise_dtype = None if noise is None else noise.dtype
@@ -130,6 +134,29 @@ class ModBiasActFn(torch.autograd.Function):
         x, pre, y = ctx.saved_tensors
         if pre is not None:
             pre = pre.float()
+        N, C, H, W = ctx.shape
+        if (not torch.is_grad_enabled() and ctx.out_dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+                and 256 % (C // 8) == 0 and x.is_contiguous(memory_format=torch.channels_last)):
+            # first-order backward (no create_graph): everything in ONE pass over dy / y / x
+            act_id, alpha, gain, clamp = ctx.cfg
+            dyc = _cl(dy).to(torch.bfloat16)
+            need_pre = pre is not None and ctx.needs_input_grad[1]
+            dev = dyc.device
+            dx = torch.empty_like(dyc)
+            dpre = torch.empty(N, C, device=dev, dtype=torch.float32) if need_pre else None
+            db_n = torch.empty(N, C, device=dev, dtype=torch.float32) if (ctx.bias_dtype is not None and ctx.needs_input_grad[3]) else None
+            dnz = torch.empty(N, H, W, device=dev, dtype=torch.float32) if (ctx.noise_shape is not None and ctx.needs_input_grad[2]) else None
+            pre_c = None if pre is None else pre.contiguous()
+            call("icgan_mod_bias_act_bwd", ptr(dyc), ptr(y if y is not None else dyc), ptr(x) if need_pre else None, ptr(pre_c),
+                 ptr(dx), ptr(dpre), ptr(db_n), ptr(dnz), N, H * W, C, act_id, float(alpha), float(gain), float(clamp),
+                 dt(dyc), stream_ptr())
+            dnoise = dbias = None
+            if dnz is not None:
+                dnoise = dnz.sum(0, keepdim=True) if ctx.noise_shape[0] == 1 and N != 1 else dnz
+                dnoise = dnoise.reshape(ctx.noise_shape).to(ctx.noise_dtype)
+            if db_n is not None:
+                dbias = db_n.sum(0).to(ctx.bias_dtype)
+            return (dx if ctx.needs_input_grad[0] else None), dpre, dnoise, dbias, None, None, None, None
         t = _ActGradFn.apply(dy, y, *ctx.cfg)  # gradient w.r.t. the pre-activation
         dx = dpre = dnoise = dbias = None
         if ctx.needs_input_grad[0]:
@@ -137,12 +164,12 @@ class ModBiasActFn(torch.autograd.Function):
         if pre is not None and ctx.needs_input_grad[1]:
             dpre = ChanDotFn.apply(t, x)
         if ctx.noise_shape is not None and ctx.needs_input_grad[2]:
-            dnoise = t.float().sum(dim=1, keepdim=True)
+            dnoise = t.sum(dim=1, keepdim=True, dtype=torch.float32)  # fp32 accumulate, no widened copy of t
             if ctx.noise_shape[0] == 1 and dnoise.shape[0] != 1:
                 dnoise = dnoise.sum(dim=0, keepdim=True)
             dnoise = dnoise.reshape(ctx.noise_shape).to(ctx.noise_dtype)
         if ctx.bias_dtype is not None and ctx.needs_input_grad[3]:
-            dbias = t.float().sum([0, 2, 3]).to(ctx.bias_dtype)
+            dbias = t.sum([0, 2, 3], dtype=torch.float32).to(ctx.bias_dtype)
         return dx, dpre, dnoise, dbias, None, None, None, None
 
 

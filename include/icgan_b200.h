@@ -272,6 +272,14 @@ int icgan_bias_act_nhwc(const void* x, const void* yref, void* y, const float* b
                         const float* noise, const float* noise_strength, int noise_per_sample, int N, int64_t hw, int C,
                         int grad, int act, float alpha, float gain, float clamp, int dtype, void* stream);
 
+/* First-order backward of icgan_bias_act_nhwc's forward in one pass (replaces the reference's bias_act grad kernel,
+ * fma backward and their reductions, bias_act.py:230-300, fma.py:31-52), bfloat16 NHWC:
+ *   t = dy*gain*act'(y)*[|y|<clamp]; dx = t*pre_scale[n,c]; dpre[n,c] = sum_p t*x; dbias_n[n,c] = sum_p t; dnoise[n,p] = sum_c t.
+ * x / pre_scale / dpre / dbias_n / dnoise may be NULL. C/8 must divide 256. */
+int icgan_mod_bias_act_bwd(const void* dy, const void* y, const void* x, const float* pre_scale, void* dx, float* dpre,
+                           float* dbias_n, float* dnoise, int N, int64_t hw, int C, int act, float alpha, float gain,
+                           float clamp, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimiser step fused with the EMA of the generator.
  * ---------------------------------------------------------------------------------------------- */

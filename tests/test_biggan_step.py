@@ -21,13 +21,27 @@ def _load():
     return meta, {k: torch.from_numpy(data[k]) for k in data.files}
 
 
-def _check(tag, got_sd, fx, lr, param_tol_lr, buf_tol=2e-4):
+def _check(tag, got_sd, fx, lr, param_tol_lr, buf_tol=2e-4, hp=None):
+    """Parameters: |w - w_ref| <= param_tol_lr x lr on every element whose gradient is well above adam_eps (second moment
+    from the reference's own optimiser state); elements with |g| ~ adam_eps or below sit where the Adam update is steep
+    in g (d step / d g ~ lr / eps), so fp32 summation-order noise alone moves them by a sizeable fraction of lr
+    (the class embedding `shared.weight`, |g| ~ 1e-5: 0.03 x lr between the CPU oracle and the reference, 0.35 x lr on
+    the GPU) -- those are held to 1 x lr."""
     worst, bad = 0.0, []
     for k, v in got_sd.items():
         ref = fx[f"{tag}/{k}"]
         got = sample_of(v.detach().float().cpu())
-        err = (got - ref).abs().max().item()
+        diff = (got - ref).abs()
+        err = diff.max().item()
         if O.is_param(k, v):
+            vkey = f"{'G' if tag == 'G_ema' else tag}_exp_avg_sq/{k}"
+            if hp is not None and vkey in fx:
+                vhat = (fx[vkey] / (1 - hp["B2"] ** hp["n_steps"])).sqrt()
+                good = vhat > 30 * hp["adam_eps"]
+                err = diff[good].max().item() if good.any() else 0.0
+                loose = diff[~good].max().item() if (~good).any() else 0.0
+                if loose > 1.0 * lr:
+                    bad.append(f"{tag}.{k}: ill-conditioned elements off by {loose / lr:.3f} x lr")
             worst = max(worst, err / lr)
             if err > param_tol_lr * lr:
                 bad.append(f"{tag}.{k}: |w - w_ref| = {err / lr:.3f} x lr")
@@ -102,9 +116,9 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt):
     print(f"step {cdt}: losses {losses} vs reference {ref_losses.tolist()}")
     if cdt == torch.float32:
         assert np.allclose(np.array(losses), ref_losses, atol=2e-3 * max(1.0, np.abs(ref_losses).max()))
-        wg = _check("G", G.state_dict(), fx, hp["G_lr"], 0.1)
-        wd = _check("D", D.state_dict(), fx, hp["D_lr"], 0.1)
-        we = _check("G_ema", G_ema.state_dict(), fx, hp["G_lr"], 0.1)
+        wg = _check("G", G.state_dict(), fx, hp["G_lr"], 0.1, hp=hp)
+        wd = _check("D", D.state_dict(), fx, hp["D_lr"], 0.1, hp=hp)
+        we = _check("G_ema", G_ema.state_dict(), fx, hp["G_lr"], 0.1, hp=hp)
         print(f"step fp32: worst |w - w_ref| / lr: G {wg:.3e}, D {wd:.3e}, G_ema {we:.3e}")
         for tag, net in (("G", G), ("D", D)):
             for k, p in net.named_parameters():

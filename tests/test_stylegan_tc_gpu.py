@@ -13,6 +13,10 @@ def _rel(a, b):
     return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20))
 
 
+def _rel_l2(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+
 CONV_CASES = [
     # name, transpose, k, stride, pad, Ci, Co, H
     ("same3x3", False, 3, 1, 1, 32, 64, 16),
@@ -126,7 +130,7 @@ def test_upfirdn2d_fused_epilogue(cuda_device, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_modulation_ops_first_and_second_order(cuda_device, dtype):
     from ic_gan_b200.stylegan2.ops import elementwise as E
-    N, C, H = 3, 32, 9
+    N, C, H = 3, 64, 9
     g = torch.Generator(device=cuda_device).manual_seed(2)
     x = torch.randn(N, C, H, H, device=cuda_device, generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
     s = torch.rand(N, C, device=cuda_device, generator=g) + 0.5
@@ -150,10 +154,19 @@ def test_modulation_ops_first_and_second_order(cuda_device, dtype):
     gy = torch.randn(yr.shape, device=cuda_device, generator=g)
     grads = torch.autograd.grad(y, args, gy.to(dtype), create_graph=True)
     rgrads = torch.autograd.grad(yr, rargs, gy, create_graph=True)
+    # bf16: the activation / clamp masks are taken from the ROUNDED output (as bias_act.cu does from y), so a handful of
+    # elements that round onto a boundary flip their mask: compare in relative L2, not max-abs
+    metric = _rel if dtype == torch.float32 else _rel_l2
     for name, a, b in zip("x s pre noise bias".split(), grads, rgrads):
-        assert _rel(a, b) <= tol * 3, (name, _rel(a, b))
+        assert metric(a, b) <= tol * 3, (name, metric(a, b))
+    # the fused one-pass backward (taken when no graph is being recorded) against the composed one
+    if dtype == torch.bfloat16:
+        y2 = mine(*args)
+        fused = torch.autograd.grad(y2, args, gy.to(dtype))
+        for name, a, b in zip("x s pre noise bias".split(), fused, rgrads):
+            assert _rel_l2(a, b) <= tol * 3, ("fused backward", name, _rel_l2(a, b))
     # second order: d/ds and d/dx of |d y / d s|^2 (the path-length pattern)
     sec = torch.autograd.grad(grads[1].square().sum(), [args[0], args[2]])
     rsec = torch.autograd.grad(rgrads[1].square().sum(), [rargs[0], rargs[2]])
     for name, a, b in zip(("x", "pre"), sec, rsec):
-        assert _rel(a, b) <= tol * 10, ("second order", name, _rel(a, b))
+        assert metric(a, b) <= tol * 10, ("second order", name, metric(a, b))
