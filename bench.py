@@ -501,6 +501,7 @@ def run_sg256(args):
     G_ema, _ = sg_build(dev)
     G_ema.load_state_dict(G.state_dict())
     G.train(); D.train(); G_ema.eval()
+    G.requires_grad_(False); D.requires_grad_(False)  # training_loop.py:226-238: each phase switches its own module on
     if world > 1:
         for net in (G, D):
             for t in list(net.parameters()) + list(net.buffers()):
@@ -514,6 +515,10 @@ def run_sg256(args):
     loss = sg_loss.StyleGAN2Loss(dev, G.mapping, G.synthesis, D, augment_pipe=None, style_mixing_prob=0.9,
                                  r1_gamma=0.0002 * SG["res"] ** 2 / (Bg * world), pl_batch_shrink=2, pl_decay=0.01, pl_weight=2)
     ema_beta = 0.5 ** (Bg * world / max(Bg * world * 10 / 32 * 1000, 1e-8))  # training_loop.py:528-531, cfg auto ema
+    eager_loss = loss
+    if not args.no_graphs and not args.ncu:
+        from ic_gan_b200.stylegan2.graphs import GraphedLoss
+        loss = GraphedLoss(eager_loss, {"G": G, "D": D})
     g_params, e_params = list(G.parameters()), list(G_ema.parameters())
     g_bufs, e_bufs = list(G.buffers()), list(G_ema.buffers())
     gen = torch.Generator(device=dev).manual_seed(300 + rank)
@@ -554,6 +559,27 @@ def run_sg256(args):
     if args.ncu:
         args.no_e2e = args.no_cpu_baseline = True
     note("sg256: networks built, warm-up")
+    graphed = loss is not eager_loss
+    prof_eager = None
+    if graphed:
+        # per-launch CUDA events cannot live inside a graph: the tensor-core kernel statistics of the roofline come from
+        # one instrumented EAGER cycle of 16 iterations (same kernels, same shapes), the throughput from graph replays
+        loss_g, loss = loss, eager_loss
+        for i in range(2):
+            iteration(real_dev, h_dev)
+        it_count[0] = 0
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        for i in range(16):
+            iteration(real_dev, h_dev)
+        torch.cuda.synchronize()
+        prof_eager, ops.PROFILE = ops.PROFILE, None
+        loss = loss_g
+        it_count[0] = 0
+        note("sg256: eager instrumented cycle done; capturing graphs")
+        iteration(real_dev, h_dev)  # it = 0 runs all four phases: captures them
+        torch.cuda.synchronize()
+        note("sg256: graphs captured")
     for i in range(args.warmup if args.ncu else max(args.warmup, 3)):
         iteration(real_dev, h_dev)
         torch.cuda.synchronize()
@@ -563,16 +589,19 @@ def run_sg256(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.PROFILE = [] if rank == 0 else None
-    launches0 = _lib.LAUNCHES
+    ops.PROFILE = [] if (rank == 0 and not graphed) else None
+    launches0 = _lib.LAUNCHES + (loss.replayed_launches if graphed else 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         iteration(real_dev, h_dev)
     e1.record()
     barrier()
-    launches = _lib.LAUNCHES - launches0
+    launches = _lib.LAUNCHES + (loss.replayed_launches if graphed else 0) - launches0
     prof, ops.PROFILE = ops.PROFILE, None
+    prof_steps = args.steps
+    if graphed:
+        prof, prof_steps = (prof_eager or []), 16
     t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -612,7 +641,7 @@ def run_sg256(args):
         d = per.setdefault(name, [0.0, 0.0, 0])
         d[0] += flops; d[1] += a.elapsed_time(b) * 1e-3; d[2] += 1
     kinfo = {k: {"launches": v[2], "avg_ms": v[1] / v[2] * 1e3, "tflops": v[0] / v[1] * 1e-12,
-                 "share_of_step": v[1] / (ms * 1e-3 * args.steps)} for k, v in per.items()}
+                 "share_of_step": v[1] / (ms * 1e-3 * prof_steps)} for k, v in per.items()}
     dom = max(per, key=lambda k: per[k][1]) if per else None
     roofline = None
     if dom:
@@ -631,6 +660,8 @@ def run_sg256(args):
                        "per_gpu_batch": Bg, "global_batch": Bg * world, "parallelism": f"dp{world}",
                        "schedule": "Gmain + Dmain every iteration, Greg every 4th, Dreg every 16th (lazy regularisation), "
                                    "fused Adam, G_ema", "l2": "inputs larger than L2",
+                       "launch": ("each phase replayed from a CUDA graph; roofline kernel statistics from an instrumented "
+                                  "eager cycle of the same 16 iterations") if graphed else "eager launches",
                        "step_gflop_per_image": SG_STEP_GF, "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
             "roofline": roofline,
             "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},
@@ -665,6 +696,8 @@ def main():
     ap.add_argument("--threads", type=int, default=ORACLE_THREADS, help=argparse.SUPPRESS)
     ap.add_argument("--affinity", default="", help=argparse.SUPPRESS)
     ap.add_argument("--sg-cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-graphs", action="store_true", help="sg256: issue every launch from Python instead of replaying "
+                                                             "one CUDA graph per loss phase")
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: short warm-up allowed, no e2e/cpu legs "
                                                        "(a number printed by such a run is never a bench value)")
     args = ap.parse_args()

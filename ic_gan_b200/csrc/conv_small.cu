@@ -152,6 +152,136 @@ __global__ void wgrad_small_kernel(const TB* __restrict__ big, const TS* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ 1x1, 128-bit accesses
+// The RGB-side layers of StyleGAN2 (toRGB C->3, fromRGB 3->C; networks.py:451-485, :786-790) are 1x1: pure streaming
+// over a full-resolution activation.  The generic kernels above read 2-byte elements (measured ~1 TB/s on 64-channel
+// 256x256 tensors); these read / write 16 bytes per lane.
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+// y[p][co<CS] = alpha * sum_c x[p][c] * w[co][c] + bias[co];  LP (power of two <= 32) lanes share a pixel
+template <typename TO, int CS>
+__global__ void __launch_bounds__(256)
+conv1x1_to_small_vec_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ alpha_p,
+                            const float* __restrict__ bias, TO* __restrict__ y, int64_t P, int C, int Cout, int LP) {
+  extern __shared__ float wsm[];  // [CS][C]
+  for (int i = threadIdx.x; i < CS * C; i += blockDim.x) wsm[i] = i < Cout * C ? wk[i] : 0.f;
+  __syncthreads();
+  const float alpha = alpha_p ? *alpha_p : 1.f;
+  const int lg = threadIdx.x % LP;
+  const int64_t groups = (static_cast<int64_t>(gridDim.x) * blockDim.x) / LP;
+  const int64_t iters = (P + groups - 1) / groups;
+  const int64_t g0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LP;
+  for (int64_t it = 0; it < iters; ++it) {  // uniform trip count (shuffles below)
+    const int64_t pix = g0 + it * groups;
+    const bool live = pix < P;
+    float acc[CS];
+#pragma unroll
+    for (int c = 0; c < CS; ++c) acc[c] = 0.f;
+    if (live)
+      for (int cc = lg * 8; cc < C; cc += LP * 8) {
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + pix * C + cc), v);
+#pragma unroll
+        for (int c = 0; c < CS; ++c)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[c] = fmaf(v[k], wsm[c * C + cc + k], acc[c]);
+      }
+#pragma unroll
+    for (int c = 0; c < CS; ++c)
+      for (int o = LP >> 1; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (live && lg == 0)
+#pragma unroll
+      for (int c = 0; c < CS; ++c)
+        if (c < Cout) st_from_float(y, pix * Cout + c, alpha * acc[c] + (bias ? bias[c] : 0.f));
+  }
+}
+
+// y[p][co0..co0+8) = alpha * sum_{ci<Cin<=4} x[p][ci] * w[co][ci] + bias: one 16-byte store per thread
+template <typename TI>
+__global__ void __launch_bounds__(256)
+conv1x1_from_small_vec_kernel(const TI* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ alpha_p,
+                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int64_t P, int Cin, int Cout) {
+  extern __shared__ float wsm[];  // [Cout][Cin]
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) wsm[i] = wk[i];
+  __syncthreads();
+  const float alpha = alpha_p ? *alpha_p : 1.f;
+  const int groups = Cout / 8;
+  const int64_t total = P * groups;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(t % groups);
+    const int64_t pix = t / groups;
+    float xv[kMaxSmall];
+#pragma unroll
+    for (int ci = 0; ci < kMaxSmall; ++ci) xv[ci] = ci < Cin ? ld_as_float(x, pix * Cin + ci) : 0.f;
+    uint4 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float o2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int co = g * 8 + 2 * j + e;
+        float a = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < kMaxSmall; ++ci)
+          if (ci < Cin) a = fmaf(xv[ci], wsm[co * Cin + ci], a);
+        o2[e] = alpha * a + (bias ? bias[co] : 0.f);
+      }
+      h[j] = __floats2bfloat162_rn(o2[0], o2[1]);
+    }
+    *reinterpret_cast<uint4*>(y + pix * Cout + g * 8) = pk;
+  }
+}
+
+// out(cs, c) += sum_p small[p][cs] * big[p][c]   (1x1 weight gradient with one tiny channel count)
+// block = (256 / LV pixel rows) x (LV = C/8 channel vectors); blockIdx.x = pixel slab
+template <typename TS, int CS>
+__global__ void __launch_bounds__(256)
+wgrad1x1_small_vec_kernel(const __nv_bfloat16* __restrict__ big, const TS* __restrict__ small, float* __restrict__ dwk,
+                          int64_t P, int Cb, int Cs, int small_is_x, int64_t slab) {
+  const int LV = Cb / 8, rows = 256 / LV;
+  const int lv = threadIdx.x % LV, prow = threadIdx.x / LV;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * slab, p1 = p0 + slab < P ? p0 + slab : P;
+  float acc[CS][8];
+#pragma unroll
+  for (int c = 0; c < CS; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
+  if (prow < rows)
+    for (int64_t pix = p0 + prow; pix < p1; pix += rows) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(big + pix * Cb + lv * 8), v);
+#pragma unroll
+      for (int c = 0; c < CS; ++c) {
+        const float sv = c < Cs ? ld_as_float(small, pix * Cs + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] = fmaf(sv, v[k], acc[c][k]);
+      }
+    }
+  __shared__ float red[256];
+  for (int c = 0; c < CS; ++c) {
+    if (c >= Cs) break;
+    for (int k = 0; k < 8; ++k) {
+      __syncthreads();
+      red[threadIdx.x] = acc[c][k];
+      __syncthreads();
+      if (prow == 0 && threadIdx.x < LV) {
+        float t = 0.f;
+        for (int r = 0; r < rows; ++r) t += red[r * LV + lv];
+        const int cb = lv * 8 + k;
+        float* dst = small_is_x ? dwk + static_cast<int64_t>(cb) * Cs + c : dwk + static_cast<int64_t>(c) * Cb + cb;
+        atomicAdd(dst, t);
+      }
+    }
+  }
+}
+
 // out[p][j] = x[p + tap(j)][ci(j)] for j = tap*Cs + ci < k*k*Cs, else 0   (bf16 out; thread = 8 output columns)
 template <typename TI>
 __global__ void im2col_small_kernel(const TI* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
@@ -205,6 +335,33 @@ extern "C" int icgan_conv2d_small(const void* x, const float* wk, const float* a
   SmallConvParams p{B, H, W, Cin, Cout, ksize, ksize / 2, act};
   const int taps = ksize * ksize;
   const int64_t P = static_cast<int64_t>(B) * H * W;
+  if (ksize == 1 && act == ICGAN_ACT_NONE && Cout <= kMaxSmall && Cin % 8 == 0 && in_dtype == ICGAN_BF16 &&
+      static_cast<size_t>(kMaxSmall) * Cin * 4 <= 48 * 1024) {  // C -> RGB, 128-bit loads
+    int LP = 1;
+    while (LP < 32 && LP * 8 < Cin) LP *= 2;
+    int64_t blocks = (P * LP + 255) / 256;
+    if (blocks > static_cast<int64_t>(num_sms()) * 16) blocks = static_cast<int64_t>(num_sms()) * 16;
+    const size_t smem = sizeof(float) * kMaxSmall * Cin;
+    DISPATCH_T(out_dtype, TO, {
+      conv1x1_to_small_vec_kernel<TO, kMaxSmall><<<static_cast<unsigned>(blocks), 256, smem, STREAM>>>(
+          static_cast<const __nv_bfloat16*>(x), wk, alpha_dev, bias, static_cast<TO*>(y), P, Cin, Cout, LP);
+    })
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
+  if (ksize == 1 && act == ICGAN_ACT_NONE && Cin <= kMaxSmall && Cout % 8 == 0 && out_dtype == ICGAN_BF16 &&
+      static_cast<size_t>(Cout) * Cin * 4 <= 48 * 1024) {  // RGB -> C, 128-bit stores
+    const int64_t total = P * (Cout / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
+    const size_t smem = sizeof(float) * Cout * Cin;
+    DISPATCH_T(in_dtype, TI, {
+      conv1x1_from_small_vec_kernel<TI><<<static_cast<unsigned>(blocks), 256, smem, STREAM>>>(
+          static_cast<const TI*>(x), wk, alpha_dev, bias, static_cast<__nv_bfloat16*>(y), P, Cin, Cout);
+    })
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   if (Cin <= kMaxSmall) {
     const size_t smem = sizeof(float) * static_cast<size_t>((Cout + 7) / 8 * 8) * taps * Cin;
     ICGAN_REQUIRE(smem <= 48 * 1024, "icgan_conv2d_small: weights do not fit shared memory");
@@ -237,6 +394,23 @@ extern "C" int icgan_conv2d_wgrad_small(const void* x, const void* dy, float* dw
   const int64_t P = static_cast<int64_t>(B) * H * W;
   const int small_is_x = Cin <= kMaxSmall ? 1 : 0;
   const int Cb = small_is_x ? Cout : Cin, Cs = small_is_x ? Cin : Cout;
+  const int big_dtype = small_is_x ? dy_dtype : x_dtype, small_dtype = small_is_x ? x_dtype : dy_dtype;
+  if (ksize == 1 && big_dtype == ICGAN_BF16 && Cb % 8 == 0 && Cb / 8 <= 256) {  // 1x1: 128-bit loads of the wide operand
+    int64_t blocks = static_cast<int64_t>(num_sms()) * 8;
+    const int rows = 256 / (Cb / 8);
+    if (blocks > (P + rows - 1) / rows) blocks = (P + rows - 1) / rows;
+    if (blocks < 1) blocks = 1;
+    const int64_t slab = (P + blocks - 1) / blocks;
+    blocks = (P + slab - 1) / slab;
+    const void* bigp = small_is_x ? dy : x;
+    const void* smallp = small_is_x ? x : dy;
+    DISPATCH_T(small_dtype, TS, {
+      wgrad1x1_small_vec_kernel<TS, kMaxSmall><<<static_cast<unsigned>(blocks), 256, 0, STREAM>>>(
+          static_cast<const __nv_bfloat16*>(bigp), static_cast<const TS*>(smallp), dwk, P, Cb, Cs, small_is_x, slab);
+    })
+    ICGAN_LAUNCH_CHECK();
+    return 0;
+  }
   const int threads = Cb >= 256 ? 256 : ((Cb + 31) / 32) * 32;
   int64_t blocks = static_cast<int64_t>(num_sms()) * 16;
   if (blocks > (P + 63) / 64) blocks = (P + 63) / 64;

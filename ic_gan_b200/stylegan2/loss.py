@@ -41,13 +41,24 @@ class StyleGAN2Loss(Loss):
         self.style_mixing_prob, self.r1_gamma = style_mixing_prob, r1_gamma
         self.pl_batch_shrink, self.pl_decay, self.pl_weight = pl_batch_shrink, pl_decay, pl_weight
         self.pl_mean = torch.zeros([], device=device)
+        self.device_side_mixing = False  # True: draw the style-mixing cutoff on the device (CUDA-graph capturable)
         self.stats = {}  # last value of each reported loss term (0-d device tensors; the reference hands these to
         #                  training_stats.report, loss.py:101-103,120-122,...): what a trainer reads back per iteration
 
     def run_G(self, z, c, h, sync):
         with _ddp_sync(self.G_mapping, sync):
             ws = self.G_mapping(z, c, h)
-            if self.style_mixing_prob > 0:
+            if self.style_mixing_prob > 0 and self.device_side_mixing:
+                # the same distribution (loss.py:66-70) with no host decision: cutoff ~ U{1..num_ws-1} with probability
+                # style_mixing_prob, else num_ws; latents at and after the cutoff come from a second mapping pass
+                n_ws = ws.shape[1]
+                cutoff = torch.randint(1, n_ws, [], device=ws.device)
+                cutoff = torch.where(torch.rand([], device=ws.device) < self.style_mixing_prob, cutoff,
+                                     torch.full_like(cutoff, n_ws))
+                ws2 = self.G_mapping(torch.randn_like(z), c, h, skip_w_avg_update=True)
+                keep = (torch.arange(n_ws, device=ws.device) < cutoff).reshape(1, n_ws, 1)
+                ws = torch.where(keep, ws, ws2)
+            elif self.style_mixing_prob > 0:
                 cutoff = int(torch.empty([], dtype=torch.int64).random_(1, ws.shape[1]))
                 if not bool(torch.rand([]) < self.style_mixing_prob):
                     cutoff = ws.shape[1]

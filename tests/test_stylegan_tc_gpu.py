@@ -27,6 +27,11 @@ CONV_CASES = [
     ("transposed_stride2", True, 3, 2, 0, 64, 32, 16),
     ("transposed_stride2_small", True, 3, 2, 0, 32, 32, 4),
     ("transposed_stride1", True, 3, 1, 1, 32, 48, 12),
+    # RGB-side 1x1 layers: the 128-bit streaming kernels (bf16) / generic small-channel kernels (float32)
+    ("torgb_64", False, 1, 1, 0, 64, 3, 32),
+    ("torgb_512", False, 1, 1, 0, 512, 3, 8),
+    ("torgb_96", False, 1, 1, 0, 96, 3, 16),
+    ("fromrgb_64", False, 1, 1, 0, 3, 64, 32),
 ]
 
 

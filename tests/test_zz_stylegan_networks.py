@@ -300,3 +300,42 @@ def test_bf16_blocks_on_emulated_kernels(emu):
 def test_loss_phases_on_emulated_kernels(emu, phase, gain):
     """All four phases -- both double backwards included -- through the package's own Functions."""
     _phase_vs_oracle(torch.device("cpu"), phase, gain, 5e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_graphed_phase_matches_eager(cuda_device):
+    """A loss phase replayed from a CUDA graph leaves the same gradients as the eager call (random inputs of the phase
+    switched off: zero noise strengths, no style mixing), and different inputs through the SAME graph give the eager
+    result for those inputs."""
+    from ic_gan_b200.stylegan2.graphs import GraphedLoss
+    meta, _, _ = _load()
+    g_sd = O.synth_state_dict(meta["g_shapes"], meta["g_seed"])
+    for k in g_sd:
+        if k.endswith("noise_strength"):
+            g_sd[k] = torch.zeros_like(g_sd[k])
+    G, D = _build(meta, cuda_device, num_fp16_res=2)
+    G.load_state_dict(g_sd); G.train(); D.train()
+    G.requires_grad_(False); D.requires_grad_(False)
+    for p in list(G.parameters()) + list(D.parameters()):
+        p.grad = torch.zeros_like(p)
+    z, h, x = (t.to(cuda_device) for t in inputs())
+    c0 = torch.zeros(z.shape[0], 0, device=cuda_device)
+    eager = b200_loss.StyleGAN2Loss(cuda_device, G.mapping, G.synthesis, D, style_mixing_prob=0.0)
+    graphed = GraphedLoss(b200_loss.StyleGAN2Loss(cuda_device, G.mapping, G.synthesis, D, style_mixing_prob=0.0), {"G": G, "D": D})
+
+    def grads(runner, zz, toggle):
+        for p in G.parameters():
+            p.grad.zero_()
+        if toggle:
+            G.requires_grad_(True)
+        runner.accumulate_gradients(phase="Gmain", real_img=x, real_c=c0, real_h=h, gen_z=zz, gen_c=c0, gen_h=h, sync=True, gain=1.0)
+        G.requires_grad_(False)
+        return {k: p.grad.clone() for k, p in G.named_parameters() if not k.endswith("noise_strength")}
+
+    graphed.accumulate_gradients(phase="Gmain", real_img=x, real_c=c0, real_h=h, gen_z=z, gen_c=c0, gen_h=h, sync=True, gain=1.0)
+    for zz in (z, z.flip(0) * 0.5):
+        want, got = grads(eager, zz, True), grads(graphed, zz, True)
+        for k in want:
+            if want[k].abs().max() > 0:
+                rel = float((got[k] - want[k]).norm() / want[k].norm())
+                assert rel <= 1e-2, f"{k}: graphed vs eager rel-L2 {rel:.3e}"
