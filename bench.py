@@ -558,6 +558,26 @@ def run_sg256(args):
 
     if args.ncu:
         args.no_e2e = args.no_cpu_baseline = True
+    if args.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+        loss = eager_loss
+        for _ in range(3):
+            iteration(real_dev, h_dev)
+        it_count[0] = 0
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
+            for _ in range(16):
+                iteration(real_dev, h_dev)
+            torch.cuda.synchronize()
+        rows = sorted(prof_t.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        with open(args.torch_profile, "w") as f:
+            f.write(f"# torch.profiler, 16 eager sg256 iterations (Gmain x16, Dmain x16, Greg x4, Dreg x1), {tot / 16e3:.2f} ms of "
+                    f"kernel time per iteration\n# kernel, launches, total ms, share\n")
+            for e in rows[:70]:
+                f.write(f"{e.key[:110]:110s} {e.count:7d} {e.device_time_total / 1e3:10.2f} {100 * e.device_time_total / tot:6.2f}%\n")
+        note(f"profile written: {tot / 16e3:.2f} ms kernel time per iteration")
+        return
     note("sg256: networks built, warm-up")
     graphed = loss is not eager_loss
     prof_eager = None
@@ -696,6 +716,8 @@ def main():
     ap.add_argument("--threads", type=int, default=ORACLE_THREADS, help=argparse.SUPPRESS)
     ap.add_argument("--affinity", default="", help=argparse.SUPPRESS)
     ap.add_argument("--sg-cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--torch-profile", default="", help="sg256: write a per-kernel device-time table (torch.profiler, 16 eager "
+                                                       "iterations) to this path and exit; shares only, never a bench value")
     ap.add_argument("--no-graphs", action="store_true", help="sg256: issue every launch from Python instead of replaying "
                                                              "one CUDA graph per loss phase")
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: short warm-up allowed, no e2e/cpu legs "
@@ -806,6 +828,20 @@ def main():
     for _ in range(args.warmup):
         step_dev()
     barrier()
+    if args.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
+            for _ in range(2):
+                step_dev()
+            torch.cuda.synchronize()
+        rows = sorted(prof_t.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        with open(args.torch_profile, "w") as f:
+            f.write(f"# torch.profiler, 2 steps of {w['name']} (per-GPU batch {Bg}, micro-batch {m}): {tot / 2e3:.2f} ms of kernel "
+                    f"time per step\n# kernel, launches, total ms, share\n")
+            for e in rows[:70]:
+                f.write(f"{e.key[:110]:110s} {e.count:7d} {e.device_time_total / 1e3:10.2f} {100 * e.device_time_total / tot:6.2f}%\n")
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -86,10 +86,15 @@ class Conv2dLayer(nn.Module):
                 self.bias = None
 
     def forward(self, x, gain=1):
-        w = (self.weight * self.weight_gain).to(x.dtype)
+        plain = self.activation == "linear" and self.bias is None and self.conv_clamp is None
+        # a linear layer without bias or clamp (the residual skip path, gain sqrt(1/2)): the output gain goes into the
+        # weights instead of costing a pass over the activation
+        w = (self.weight * (self.weight_gain * self.act_gain * gain if plain else self.weight_gain)).to(x.dtype)
         b = self.bias.to(x.dtype) if self.bias is not None else None
         x = conv2d_resample.conv2d_resample(x=x, w=w, f=self.resample_filter, up=self.up, down=self.down,
                                             padding=self.padding, flip_weight=(self.up == 1))
+        if plain:
+            return x
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         # bias + activation + gain + clamp in one pass, and ONE pass again for (dx, dbias) in the first-order backward
         return elementwise.mod_bias_act(x, bias=b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
@@ -240,7 +245,7 @@ class SynthesisBlock(nn.Module):
                 y = self.skip(x, gain=_SQRT_HALF)
                 x = self.conv0(x, next(latents), fused_modconv=fused_modconv, **layer_kwargs)
                 x = self.conv1(x, next(latents), fused_modconv=fused_modconv, gain=_SQRT_HALF, **layer_kwargs)
-                x = y.add_(x)
+                x = y + x  # (the skip output is a view produced by a custom Function: no in-place update)
             else:
                 x = self.conv0(x, next(latents), fused_modconv=fused_modconv, **layer_kwargs)
                 x = self.conv1(x, next(latents), fused_modconv=fused_modconv, **layer_kwargs)
@@ -346,7 +351,7 @@ class DiscriminatorBlock(nn.Module):
         if self.architecture == "resnet":
             y = self.skip(x, gain=_SQRT_HALF)
             x = self.conv1(self.conv0(x), gain=_SQRT_HALF)
-            x = y.add_(x)
+            x = y + x  # (the skip output is a view produced by a custom Function: no in-place update)
         else:
             x = self.conv1(self.conv0(x))
         assert x.dtype == dtype
