@@ -71,7 +71,7 @@ SIGNATURES = {
     "icgan_upfirdn2d": [vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
                         i32, vp],
     "icgan_upfirdn2d_nhwc": [vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, fp, fp, fp, i32, fp, i32,
-                             f32, f32, f32, fp, vp, i32, vp],
+                             f32, f32, f32, fp, vp, vp, vp, i32, vp],
     "icgan_modulate": [vp, fp, vp, i32, i64, i32, i32, i32, vp],
     "icgan_chan_dot": [vp, vp, fp, i32, i64, i32, i32, i32, vp],
     "icgan_bias_act_nhwc": [vp, vp, vp, fp, fp, fp, fp, i32, i32, i64, i32, i32, i32, f32, f32, f32, i32, vp],
@@ -119,6 +119,11 @@ def call(name: str, *args) -> None:
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {last_error()}")
+
+
+def float_array(values):
+    """Host float array argument."""
+    return (C.c_float * len(values))(*[float(v) for v in values])
 
 
 def int_array(values):

@@ -139,13 +139,16 @@ class Attention(nn.Module):
         self.g = which_conv(ch, ch // 2, kernel_size=1, padding=0, bias=False)
         self.o = which_conv(ch // 2, ch, kernel_size=1, padding=0, bias=False)
         self.gamma = P(torch.tensor(0.0), requires_grad=True)
+        if (ch // 8) % 8:  # e.g. ch = 96: theta / phi get zero channels up to a multiple of 8 (tensor-core eligibility)
+            self.theta.pad_out_to = self.phi.pad_out_to = 8
 
     def forward_nhwc(self, x):
         B, H, W, C = x.shape
         theta = self.theta.conv_nhwc(x)
         phi = ops.Pool2Fn.apply(self.phi.conv_nhwc(x), None, 1.0, 1)
         g = ops.Pool2Fn.apply(self.g.conv_nhwc(x), None, 1.0, 1)
-        o = ops.AttentionCoreFn.apply(theta.reshape(B, H * W, C // 8), phi.reshape(B, H * W // 4, C // 8),
+        d = theta.shape[3]  # C // 8, or that rounded up to a multiple of 8 with all-zero channels (bf16 mode)
+        o = ops.AttentionCoreFn.apply(theta.reshape(B, H * W, d), phi.reshape(B, H * W // 4, d),
                                       g.reshape(B, H * W // 4, C // 2))
         o = self.o.conv_nhwc(o.reshape(B, H, W, C // 2))
         return ops.ScaleAddFn.apply(o, x, self.gamma)

@@ -77,11 +77,16 @@ struct UpfirdnTiledParams {
   int N, C, inH, inW, outH, outW, pad0x, pad0y, flip;
   float gain;
   PostArgs post;
+  // rank-1 filters (f = fy (x) fx, e.g. the [1,3,3,1] outer product of every StyleGAN2 resampling filter): the kernel
+  // filters each row horizontally as it enters the sliding window and vertically per output -- 8 instead of 16
+  // tap-FMAs (and bf16 unpacks) per output vector, which is what makes the pass HBM-bound instead of issue-bound
+  int separable;
+  float fx[4], fy[4];  // already flipped / gain-scaled like fs[] below (gain on fy)
 };
 
 // Square up/down factors, fh = fw = 4 (every resampling filter StyleGAN2 uses: [1,3,3,1] outer product).
 // Tile: TOH x TOW outputs x (8 lanes x 16 bytes) channels.  Thread = (lane, column, row group).
-template <typename T, int UP, int DOWN, int TOH, int TOW>
+template <typename T, int UP, int DOWN, int TOH, int TOW, bool SEP>
 __global__ void __launch_bounds__(256, 2)
 upfirdn2d_tiled_kernel(const T* __restrict__ x, const float* __restrict__ f, T* __restrict__ y, const UpfirdnTiledParams p) {
   constexpr int NV = Pack<T>::N;          // channels per lane
@@ -149,8 +154,29 @@ upfirdn2d_tiled_kernel(const T* __restrict__ x, const float* __restrict__ f, T* 
   };
   const int row_first = rg * ROWS;
   int u_cur = uy0 + row_first * DOWN;
+  // separable form: hwin[r] = horizontally filtered row (float), filled as rows enter the window
+  float hwin[F][NV];
+  auto load_hrow = [&](int u_row, float (&dst)[NV]) {
+    uint4 raw[F];
+    load_row(u_row, raw);
 #pragma unroll
-  for (int r = 0; r < F; ++r) load_row(u_cur + r, win[r]);
+    for (int k = 0; k < NV; ++k) dst[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < F; ++t) {
+      float xv[NV];
+      Pack<T>::unpack(raw[t], xv);
+      const float w = p.fx[t];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) dst[k] = fmaf(xv[k], w, dst[k]);
+    }
+  };
+  if constexpr (SEP) {
+#pragma unroll
+    for (int r = 0; r < F; ++r) load_hrow(u_cur + r, hwin[r]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < F; ++r) load_row(u_cur + r, win[r]);
+  }
   const float ns = p.post.noise_strength ? *p.post.noise_strength : 1.f;
 #pragma unroll
   for (int ro = 0; ro < ROWS; ++ro) {
@@ -158,16 +184,25 @@ upfirdn2d_tiled_kernel(const T* __restrict__ x, const float* __restrict__ f, T* 
     float acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+    if constexpr (SEP) {
 #pragma unroll
-    for (int r = 0; r < F; ++r)
+      for (int r = 0; r < F; ++r) {
+        const float w = p.fy[r];
 #pragma unroll
-      for (int t = 0; t < F; ++t) {
-        const float w = fs[r * F + t];
-        float xv[NV];
-        Pack<T>::unpack(win[r][t], xv);
-#pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = fmaf(xv[k], w, acc[k]);
+        for (int k = 0; k < NV; ++k) acc[k] = fmaf(hwin[r][k], w, acc[k]);
       }
+    } else {
+#pragma unroll
+      for (int r = 0; r < F; ++r)
+#pragma unroll
+        for (int t = 0; t < F; ++t) {
+          const float w = fs[r * F + t];
+          float xv[NV];
+          Pack<T>::unpack(win[r][t], xv);
+#pragma unroll
+          for (int k = 0; k < NV; ++k) acc[k] = fmaf(xv[k], w, acc[k]);
+        }
+    }
     if (c_ok && oy < p.outH && ox < p.outW) {
       const int64_t pix = (static_cast<int64_t>(n) * p.outH + oy) * p.outW + ox;
       if (p.post.act) {
@@ -197,12 +232,21 @@ upfirdn2d_tiled_kernel(const T* __restrict__ x, const float* __restrict__ f, T* 
     // advance the window by DOWN rows
     if (ro + 1 < ROWS) {
       u_cur += DOWN;
+      if constexpr (SEP) {
 #pragma unroll
-      for (int r = 0; r + DOWN < F; ++r)
+        for (int r = 0; r + DOWN < F; ++r)
 #pragma unroll
-        for (int t = 0; t < F; ++t) win[r][t] = win[r + DOWN][t];
+          for (int k = 0; k < NV; ++k) hwin[r][k] = hwin[r + DOWN][k];
 #pragma unroll
-      for (int r = F - DOWN; r < F; ++r) load_row(u_cur + r, win[r]);
+        for (int r = F - DOWN; r < F; ++r) load_hrow(u_cur + r, hwin[r]);
+      } else {
+#pragma unroll
+        for (int r = 0; r + DOWN < F; ++r)
+#pragma unroll
+          for (int t = 0; t < F; ++t) win[r][t] = win[r + DOWN][t];
+#pragma unroll
+        for (int r = F - DOWN; r < F; ++r) load_row(u_cur + r, win[r]);
+      }
     }
   }
 }
@@ -395,20 +439,20 @@ static int grid_for(int64_t work) {
   return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
-template <typename T, int UP, int DOWN, int TOH, int TOW>
+template <typename T, int UP, int DOWN, int TOH, int TOW, bool SEP>
 static int launch_upfirdn_tiled(const void* x, const float* f, void* y, const UpfirdnTiledParams& p, cudaStream_t st) {
   constexpr int NV = 16 / sizeof(T), CB = 8 * NV;
   constexpr int PH = (TOH * DOWN + 4 - 1 + UP - 1) / UP + 1, PW = (TOW * DOWN + 4 - 1 + UP - 1) / UP + 1;
   constexpr size_t smem = static_cast<size_t>(PH) * PW * 8 * 16;
   static unsigned long long configured = 0ull;
   if (first_use_on_this_device(&configured)) {
-    ICGAN_CUDA(cudaFuncSetAttribute(upfirdn2d_tiled_kernel<T, UP, DOWN, TOH, TOW>,
+    ICGAN_CUDA(cudaFuncSetAttribute(upfirdn2d_tiled_kernel<T, UP, DOWN, TOH, TOW, SEP>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   const int64_t blocks = static_cast<int64_t>(p.N) * ((p.outH + TOH - 1) / TOH) * ((p.outW + TOW - 1) / TOW) *
                          ((p.C + CB - 1) / CB);
   ICGAN_REQUIRE(blocks > 0 && blocks < (1ll << 31), "icgan_upfirdn2d_nhwc: grid too large");
-  upfirdn2d_tiled_kernel<T, UP, DOWN, TOH, TOW><<<static_cast<unsigned>(blocks), 256, smem, st>>>(
+  upfirdn2d_tiled_kernel<T, UP, DOWN, TOH, TOW, SEP><<<static_cast<unsigned>(blocks), 256, smem, st>>>(
       static_cast<const T*>(x), f, static_cast<T*>(y), p);
   ICGAN_LAUNCH_CHECK();
   return 0;
@@ -417,9 +461,15 @@ static int launch_upfirdn_tiled(const void* x, const float* f, void* y, const Up
 template <typename T>
 static int dispatch_upfirdn_tiled(const void* x, const float* f, void* y, const UpfirdnTiledParams& p, int up, int down,
                                   cudaStream_t st) {
-  if (up == 1 && down == 1) return launch_upfirdn_tiled<T, 1, 1, 8, 32>(x, f, y, p, st);
-  if (up == 2 && down == 1) return launch_upfirdn_tiled<T, 2, 1, 8, 32>(x, f, y, p, st);
-  if (up == 1 && down == 2) return launch_upfirdn_tiled<T, 1, 2, 8, 16>(x, f, y, p, st);
+  if (p.separable) {
+    if (up == 1 && down == 1) return launch_upfirdn_tiled<T, 1, 1, 8, 32, true>(x, f, y, p, st);
+    if (up == 2 && down == 1) return launch_upfirdn_tiled<T, 2, 1, 8, 32, true>(x, f, y, p, st);
+    if (up == 1 && down == 2) return launch_upfirdn_tiled<T, 1, 2, 8, 16, true>(x, f, y, p, st);
+  } else {
+    if (up == 1 && down == 1) return launch_upfirdn_tiled<T, 1, 1, 8, 32, false>(x, f, y, p, st);
+    if (up == 2 && down == 1) return launch_upfirdn_tiled<T, 2, 1, 8, 32, false>(x, f, y, p, st);
+    if (up == 1 && down == 2) return launch_upfirdn_tiled<T, 1, 2, 8, 16, false>(x, f, y, p, st);
+  }
   icgan::set_error("icgan_upfirdn2d_nhwc: (up, down) must be (1,1), (2,1) or (1,2)");
   return -1;
 }
@@ -428,8 +478,10 @@ extern "C" int icgan_upfirdn2d_nhwc(const void* x, const float* f4x4, void* y, i
                                     int down, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                                     const float* pre_scale, const float* noise, const float* noise_strength,
                                     int noise_per_sample, const float* bias, int act, float alpha, float act_gain,
-                                    float clamp, const float* s2, void* y2, int dtype, void* stream) {
+                                    float clamp, const float* s2, void* y2, const float* fx_host, const float* fy_host,
+                                    int dtype, void* stream) {
   ICGAN_REQUIRE(x && f4x4 && y && N > 0 && C > 0, "icgan_upfirdn2d_nhwc: bad arguments");
+  ICGAN_REQUIRE((fx_host == nullptr) == (fy_host == nullptr), "icgan_upfirdn2d_nhwc: fx_host and fy_host go together");
   ICGAN_REQUIRE(act == 0 || act == 1 || act == 3, "icgan_upfirdn2d_nhwc: epilogue activation must be 0 (none), 1 or 3");
   ICGAN_REQUIRE((s2 == nullptr) == (y2 == nullptr), "icgan_upfirdn2d_nhwc: s2 and y2 go together");
   UpfirdnTiledParams p{};
@@ -438,6 +490,11 @@ extern "C" int icgan_upfirdn2d_nhwc(const void* x, const float* f4x4, void* y, i
   p.outH = (inH * up + pady0 + pady1 - 4 + down) / down;
   ICGAN_REQUIRE(p.outW >= 1 && p.outH >= 1, "icgan_upfirdn2d_nhwc: empty output");
   p.pad0x = padx0; p.pad0y = pady0; p.flip = flip; p.gain = gain;
+  p.separable = fx_host != nullptr;
+  for (int t = 0; t < 4; ++t) {  // same orientation and gain as the 2-D table the kernel builds from f4x4
+    p.fx[t] = p.separable ? fx_host[flip ? t : 3 - t] : 0.f;
+    p.fy[t] = p.separable ? fy_host[flip ? t : 3 - t] * gain : 0.f;
+  }
   p.post = PostArgs{pre_scale, noise, noise_strength, bias, s2, y2, noise_per_sample, act, alpha, act_gain, clamp};
   if (!act && (pre_scale || noise || bias)) { icgan::set_error("icgan_upfirdn2d_nhwc: epilogue inputs need act != 0"); return -1; }
   const int nv = dtype == ICGAN_F32 ? 4 : 8;

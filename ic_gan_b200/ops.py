@@ -73,6 +73,7 @@ class SNState:
         self.fresh = False
         self.key = None
         self.version = None
+        self.co_pad = 0
 
     # -- buffers -------------------------------------------------------------------------------------------------
     def _ensure(self, compute_dtype):
@@ -91,6 +92,12 @@ class SNState:
             return
         co, ci, k, _ = w.shape
         dev, bf = w.device, compute_dtype == torch.bfloat16
+        # `pad_out_to` (set by Attention on its theta / phi convs): the layer computes extra all-zero output channels so
+        # that Cout is a multiple of 8 -- ch/8 = 12 at ch = 96 would otherwise push the conv AND the attention products
+        # onto the CUDA-core kernels (38 % of the ic-128 step, profiles/r02_ic128_kernel_table.txt).  Zero channels change
+        # nothing in theta.phi^T; the master weight and its gradient keep their [Cout, Cin] shape.
+        self.co_pad = ((-co) % int(getattr(self.module, "pad_out_to", 0))) if (bf and getattr(self.module, "pad_out_to", 0)) else 0
+        co = co + self.co_pad
         # forward operand: how the layer runs (see _conv_forward)
         #   "tc"    tensor-core implicit GEMM on [Cout,k,k,Cin] bf16
         #   "col"   Cin<=4 (RGB in): explicit im2col to KP=16/32 columns, then the tensor-core kernel as a 1x1 conv
@@ -156,6 +163,13 @@ class SNState:
             return
         self.version = stamp
         co, ci, k, _ = w.shape
+        if self.co_pad:  # zero-padded output channels: relayout in float32, pad, narrow (small 1x1 weights only)
+            f32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32)
+            d32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32)
+            call("icgan_sn_prepare_weight", ptr(w), None, ptr(f32), ptr(d32), co, ci, k, L.F32, stream_ptr())
+            self.wk_fwd = torch.nn.functional.pad(f32, (0, 0, 0, 0, 0, 0, 0, self.co_pad)).to(torch.bfloat16)
+            self.wk_dgrad = torch.nn.functional.pad(d32, (0, self.co_pad)).to(torch.bfloat16).contiguous()
+            return
         if self.mode == "tc" and self.mode_d == "tc":  # both operands are plain bf16 relayouts: write them directly
             self.wk_fwd = torch.empty(co, k, k, ci, device=w.device, dtype=torch.bfloat16)
             self.wk_dgrad = torch.empty(ci, k, k, co, device=w.device, dtype=torch.bfloat16)
@@ -248,7 +262,7 @@ def _conv_forward(x: Tensor, st: SNState, bias, residual, res_shift: int, act: i
     alpha = st.alpha if (snap is None or not st.use_sn) else snap[2][1:]
     wk, mode, kp = (st.wk_fwd, st.mode, st.kp) if not dgrad else (st.wk_dgrad, st.mode_d, st.kp_d)
     w = st.module.weight
-    cout, k = (w.shape[0], w.shape[2]) if not dgrad else (w.shape[1], w.shape[2])
+    cout, k = (w.shape[0] + st.co_pad, w.shape[2]) if not dgrad else (w.shape[1], w.shape[2])
     if stats is not None and mode != "tc":
         raise RuntimeError("fused batch-norm statistics need the tensor-core conv path")
     if mode == "tc":
@@ -364,6 +378,8 @@ class SNConvFn(torch.autograd.Function):
             if st.mode == "tc":
                 G = torch.zeros(cout, k, k, cin, device=dy.device, dtype=torch.float32)
                 _wgrad_tc(x, dyc, G, B, H, W, cin, cout, k)
+                if st.co_pad:
+                    G = G[:cout - st.co_pad].contiguous()
             elif st.mode == "col":
                 Gc = torch.zeros(cout, st.kp, device=dy.device, dtype=torch.float32)
                 _wgrad_tc(xcol if xcol is not None else _im2col(x, k, st.kp), dyc, Gc, B, H, W, st.kp, cout, 1)

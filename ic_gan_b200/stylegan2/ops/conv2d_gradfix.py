@@ -72,6 +72,13 @@ def _tc_ok(ci, co):
     return ci % 16 == 0 and co % 8 == 0
 
 
+def _pad_last(t, mult):
+    """Zero-pad the channel (last) dimension up to a multiple of `mult` (the 513-channel input of D's epilogue conv,
+    networks.py:963: minibatch-std adds one channel; a few zero channels buy the tensor-core path)."""
+    r = (-t.shape[-1]) % mult
+    return t if r == 0 else torch.nn.functional.pad(t, (0, r))
+
+
 # ------------------------------------------------------------------------------------------------- raw launches
 def _timed(kind, flops, fn):
     """bench.py sets ops.PROFILE to a list: CUDA events around every tensor-core launch (the live roofline source)."""
@@ -127,6 +134,13 @@ def _conv_core(x, w, stride, pad):
     co, k = w.shape[0], w.shape[2]
     ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     wk = w.detach().float().permute(0, 2, 3, 1).contiguous()  # [Co,k,k,Ci]
+    if not _tc_ok(ci, co) and min(ci, co) > 16 and x.dtype in (torch.bfloat16, torch.float32) and k * k <= 16:
+        xp = _pad_last(x, 16)
+        wp = _pad_last(wk, 16)
+        if co % 8:
+            wp = torch.nn.functional.pad(wp, (0, 0, 0, 0, 0, 0, 0, (-co) % 8))
+        wfull = wp.permute(0, 3, 1, 2)  # back to [Co', Ci', k, k] for the recursive call
+        return _conv_core(xp, wfull, stride, pad)[..., :co].contiguous()
     if _tc_ok(ci, co) and x.dtype in (torch.bfloat16, torch.float32) and k * k <= 16:
         if stride == 1 and pad == k // 2 and k in (1, 3):
             return _run_tc(x, wk, lambda a, b, y, r: _launch_same(a, b, y, r, k), (B, ho, wo, co))
@@ -187,6 +201,10 @@ def _wgrad_core(x, dy, stride, pad, k, transpose):
     a, b = (dy, x) if not transpose else (x, dy)  # a indexes the result's rows and walks the tile domain unshifted
     B, ha, wa, ca = a.shape
     _, hb, wb, cb = b.shape
+    if not _tc_ok(cb, ca) and min(ca, cb) > 16 and a.dtype in (torch.bfloat16, torch.float32) and k * k <= 16:
+        ap, bp = _pad_last(a, 8), _pad_last(b, 16)
+        xx, dd = (bp, ap) if not transpose else (ap, bp)
+        return _wgrad_core(xx, dd, stride, pad, k, transpose)[:ca, :cb]
     if _tc_ok(cb, ca) and a.dtype in (torch.bfloat16, torch.float32) and k * k <= 16:
         G = torch.zeros(ca, k, k, cb, device=x.device, dtype=torch.float32)
         taps = [(kh - pad, kw - pad) for kh in range(k) for kw in range(k)]

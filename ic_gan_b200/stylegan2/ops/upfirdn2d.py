@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..._lib import call, dt, ptr, stream_ptr
+from ..._lib import call, dt, float_array, ptr, stream_ptr
 
 
 # ------------------------------------------------------------------------------------------------- argument geometry
@@ -82,6 +82,26 @@ def _fast_ok(x, f2d, up, down):
             and x.shape[1] % nv == 0)
 
 
+_factor_cache = {}
+
+
+def _factors(f2d):
+    """(fx, fy) host tuples if the 4x4 filter is an outer product fy (x) fx (every filter setup_filter builds from 1-D
+    taps), else None.  One device->host read per filter buffer, cached on (pointer, version): it happens during the
+    eager warm-up, never inside a captured graph."""
+    key = (f2d.data_ptr(), f2d._version)
+    if key not in _factor_cache:
+        h = f2d.detach().double().cpu()
+        total = float(h.sum())
+        out = None
+        if total != 0.0:
+            fy, fx = h.sum(1) / total, h.sum(0)
+            if float((torch.outer(fy, fx) - h).abs().max()) <= 1e-7 * float(h.abs().max()):
+                out = (tuple(fx.tolist()), tuple(fy.tolist()))
+        _factor_cache[key] = out
+    return _factor_cache[key]
+
+
 def _run(x, f2d, up, down, pad, flip, gain):
     N, C, H, W = x.shape
     fh, fw = f2d.shape
@@ -91,8 +111,10 @@ def _run(x, f2d, up, down, pad, flip, gain):
     if _fast_ok(x, f2d, up, down):  # channels-last tiled kernel (a non-channels-last input is re-laid-out once)
         xin = x.contiguous(memory_format=torch.channels_last)
         y = torch.empty((N, C, oh, ow), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        fac = _factors(f2d)
         call("icgan_upfirdn2d_nhwc", ptr(xin), ptr(f2d), ptr(y), N, C, H, W, up[0], down[0], pad[0], pad[1], pad[2], pad[3],
-             int(flip), float(gain), None, None, None, 0, None, 0, 0.0, 1.0, -1.0, None, None, dt(x), stream_ptr())
+             int(flip), float(gain), None, None, None, 0, None, 0, 0.0, 1.0, -1.0, None, None,
+             float_array(fac[0]) if fac else None, float_array(fac[1]) if fac else None, dt(x), stream_ptr())
         return y
     cl = _channels_last(x)
     xin = x.contiguous(memory_format=torch.channels_last) if cl else x.contiguous()

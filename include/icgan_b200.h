@@ -253,12 +253,14 @@ int icgan_upfirdn2d(const void* x, const float* f, void* y, int N, int C, int in
  * noise_strength (device scalar, NULL = 1), bias [C], s2 [N,C] (styles of the NEXT layer; y2 = y*s2 is its modulated
  * input). act: 0 = no epilogue, 1 = linear, 3 = lrelu (bias_act.py:26-99 ids); clamp < 0 disables clamping. */
 /* Shared-memory-tiled upfirdn2d (upfirdn2d.cu:100-203 `upfirdn2d_kernel_small` re-designed for NHWC), 4x4 filter,
- * (up, down) in {(1,1), (2,1), (1,2)}:  y = epilogue(gain * upfirdn(x)); x [N,inH,inW,C], y [N,outH,outW,C]. */
+ * (up, down) in {(1,1), (2,1), (1,2)}:  y = epilogue(gain * upfirdn(x)); x [N,inH,inW,C], y [N,outH,outW,C].
+ * fx_host / fy_host (HOST arrays of 4 floats, or both NULL): when the filter is the outer product fy (x) fx -- every
+ * resampling filter setup_filter builds from 1-D taps -- pass the factors and the kernel filters separably. */
 int icgan_upfirdn2d_nhwc(const void* x, const float* f4x4, void* y, int N, int C, int inH, int inW, int up, int down,
                          int padx0, int padx1, int pady0, int pady1, int flip, float gain, const float* pre_scale,
                          const float* noise, const float* noise_strength, int noise_per_sample, const float* bias,
-                         int act, float alpha, float act_gain, float clamp, const float* s2, void* y2, int dtype,
-                         void* stream);
+                         int act, float alpha, float act_gain, float clamp, const float* s2, void* y2,
+                         const float* fx_host, const float* fy_host, int dtype, void* stream);
 /* y[n,p,c] = x[n,p,c] * s[n,c]  (networks.py:78 `x * styles`), optional float32 <-> bfloat16 cast. C % 8 == 0. */
 int icgan_modulate(const void* x, const float* s, void* y, int N, int64_t hw, int C, int in_dtype, int out_dtype,
                    void* stream);

@@ -132,7 +132,7 @@ def icgan_upfirdn2d(x, f, y, N, C, inH, inW, fh, fw, upx, upy, downx, downy, px0
 
 
 def icgan_upfirdn2d_nhwc(x, f, y, N, C, inH, inW, up, down, px0, px1, py0, py1, flip, gain, pre, noise, ns, nps, bias, act,
-                         alpha, act_gain, clamp, s2, y2, dtype, stream):
+                         alpha, act_gain, clamp, s2, y2, fx_host, fy_host, dtype, stream):
     assert act == 0 and y2 is None, "emulator: the fused epilogue of icgan_upfirdn2d_nhwc is exercised on the GPU only"
     icgan_upfirdn2d(x, f, y, N, C, inH, inW, 4, 4, up, up, down, down, px0, px1, py0, py1, flip, gain, 1, dtype, stream)
 

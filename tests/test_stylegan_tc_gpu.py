@@ -89,20 +89,20 @@ def test_tiled_upfirdn2d(cuda_device, case, dtype):
     up, down, pad, H, C = case
     g = torch.Generator(device=cuda_device).manual_seed(5)
     x = torch.randn(2, C, H, H + 3, device=cuda_device, generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
-    f = U.setup_filter([1, 3, 3, 1], device=cuda_device)
-    for flip in (False, True):
+    f0 = U.setup_filter([1, 3, 3, 1], device=cuda_device)
+    general = f0 * torch.arange(1, 17, device=cuda_device).reshape(4, 4) / 8               # rank 4: 2-D tap loop
+    rank1 = torch.outer(torch.tensor([1., 2., 4., 3.]), torch.tensor([2., 1., 5., 3.])).to(cuda_device) / 40  # separable path
+    for flip, f in ((False, general), (True, general), (False, rank1), (True, rank1), (False, f0)):
         xg = x.clone().requires_grad_(True)
-        y = U.upfirdn2d(xg, f * torch.arange(1, 17, device=cuda_device).reshape(4, 4) / 8, up=up, down=down, padding=list(pad),
-                        flip_filter=flip, gain=up * up)
-        ref = _fir_ref(x.float(), f * torch.arange(1, 17, device=cuda_device).reshape(4, 4) / 8, up, down, pad, flip, up * up)
+        y = U.upfirdn2d(xg, f, up=up, down=down, padding=list(pad), flip_filter=flip, gain=up * up)
+        ref = _fir_ref(x.float(), f, up, down, pad, flip, up * up)
         assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
         tol = 1e-5 if dtype == torch.float32 else 1e-2
         assert _rel(y, ref) <= tol, (flip, _rel(y, ref))
         gy = torch.randn(ref.shape, device=cuda_device, generator=g)
         (dx,) = torch.autograd.grad(y, xg, gy.to(dtype))
         xr = x.float().requires_grad_(True)
-        (dxr,) = torch.autograd.grad(_fir_ref(xr, f * torch.arange(1, 17, device=cuda_device).reshape(4, 4) / 8, up, down, pad,
-                                              flip, up * up), xr, gy)
+        (dxr,) = torch.autograd.grad(_fir_ref(xr, f, up, down, pad, flip, up * up), xr, gy)
         assert _rel(dx, dxr) <= tol * 2, (flip, "adjoint", _rel(dx, dxr))
 
 
@@ -122,8 +122,10 @@ def test_upfirdn2d_fused_epilogue(cuda_device, dtype):
     bias = torch.randn(C, device=cuda_device, generator=g)
     y = torch.empty(N, 16, 16, C, device=cuda_device, dtype=dtype)
     y2 = torch.empty_like(y)
+    from ic_gan_b200._lib import float_array
+    taps = [0.125, 0.375, 0.375, 0.125]
     call("icgan_upfirdn2d_nhwc", ptr(x), ptr(f), ptr(y), N, C, H, H, 1, 1, 1, 1, 1, 1, 0, 4.0, ptr(pre), ptr(noise), ptr(ns), 1,
-         ptr(bias), 3, 0.2, 2 ** 0.5, 1.5, ptr(s2), ptr(y2), dt(x), stream_ptr())
+         ptr(bias), 3, 0.2, 2 ** 0.5, 1.5, ptr(s2), ptr(y2), float_array(taps), float_array(taps), dt(x), stream_ptr())
     base = _fir_ref(x.float().permute(0, 3, 1, 2), f, 1, 1, (1, 1, 1, 1), False, 4.0)
     t = base * pre[:, :, None, None] + 0.3 * noise[:, None] + bias[None, :, None, None]
     ref = (F.leaky_relu(t, 0.2) * 2 ** 0.5).clamp(-1.5, 1.5).permute(0, 2, 3, 1)
