@@ -233,6 +233,37 @@ def d_block(sd, prefix, x, training, cfg, preact: bool, down: bool):
     return h + s
 
 
+def g_block_deep(sd, prefix, x, y, training, cfg, out_channels: int, upsample: bool):
+    """BigGANdeep.GBlock.forward (BigGANdeep.py:67-85): 1x1 down, BN-ReLU, (x2 nearest), 3x3, 3x3, 1x1 up; the shortcut
+    drops channels instead of projecting them."""
+    h = sn_conv(sd, prefix + "conv1.", F.relu(ccbn(sd, prefix + "bn1.", x, y, training, cfg)), training, cfg.SN_eps, 0)
+    h = F.relu(ccbn(sd, prefix + "bn2.", h, y, training, cfg))
+    if x.shape[1] != out_channels:
+        x = x[:, :out_channels]
+    if upsample:
+        h, x = F.interpolate(h, scale_factor=2), F.interpolate(x, scale_factor=2)
+    h = sn_conv(sd, prefix + "conv2.", h, training, cfg.SN_eps, 1)
+    h = sn_conv(sd, prefix + "conv3.", F.relu(ccbn(sd, prefix + "bn3.", h, y, training, cfg)), training, cfg.SN_eps, 1)
+    h = sn_conv(sd, prefix + "conv4.", F.relu(ccbn(sd, prefix + "bn4.", h, y, training, cfg)), training, cfg.SN_eps, 0)
+    return h + x
+
+
+def d_block_deep(sd, prefix, x, training, cfg, down: bool):
+    """BigGANdeep.DBlock.forward (BigGANdeep.py:431-451): relu-1x1, relu-3x3, relu-3x3, relu, (avg-pool), 1x1; shortcut =
+    (avg-pool) then concat with conv_sc when the channel count grows."""
+    eps = cfg.SN_eps
+    h = sn_conv(sd, prefix + "conv1.", F.relu(x), training, eps, 0)
+    h = sn_conv(sd, prefix + "conv2.", F.relu(h), training, eps, 1)
+    h = F.relu(sn_conv(sd, prefix + "conv3.", F.relu(h), training, eps, 1))
+    if down:
+        h = F.avg_pool2d(h, 2)
+    h = sn_conv(sd, prefix + "conv4.", h, training, eps, 0)
+    s = F.avg_pool2d(x, 2) if down else x
+    if (prefix + "conv_sc.weight") in sd:
+        s = torch.cat([s, sn_conv(sd, prefix + "conv_sc.", s, training, eps, 0)], 1)
+    return h + s
+
+
 # ----------------------------------------------------------------------------- networks
 def generator_forward(sd, cfg: BigGANConfig, z: Tensor, label: Optional[Tensor], feats: Optional[Tensor],
                       training: bool) -> Tensor:
