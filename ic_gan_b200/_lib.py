@@ -32,7 +32,7 @@ class IcganSnLayer(C.Structure):
 # name -> argtypes (all return int). Mirrors include/icgan_b200.h one to one; tests check the two stay in sync.
 SIGNATURES = {
     "icgan_conv2d_tc": [vp, vp, fp, fp, vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
-    "icgan_conv2d_tc_ex": [vp, vp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+    "icgan_conv2d_tc_ex": [vp, vp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                            i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_tc_ex": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
     "icgan_conv2d_rgb_tc": [vp, vp, fp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],

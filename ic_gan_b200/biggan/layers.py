@@ -91,6 +91,11 @@ class SNConv2d(nn.Conv2d, SN):
         return ops.SNConvFn.apply(x, self.weight, self.bias, residual, st, res_shift, act,
                                   out_dtype if out_dtype is not None else x.dtype, stats, mask_input, act_bwd_in_consumer)
 
+    def upconv_nhwc(self, x):
+        """conv3x3(nearest_up2(x)) in sub-pixel form (ops.UpConvFn): x is the LOW-resolution tensor."""
+        st = self._sn_ready()
+        return ops.UpConvFn.apply(x, self.weight, self.bias, st)
+
     def bn_stats_buffer(self, x):
         """float32 [2*Cout] accumulator if this conv can emit the batch statistics of its output from its epilogue
         (tensor-core path, training, Cout % 32 == 0), else None."""
@@ -237,9 +242,14 @@ class GBlock(nn.Module):
         producing conv's epilogue; they travel with the tensor as the attribute `_icgan_bn = (sums, shift)`."""
         up = bool(self.upsample)
         pre = getattr(x, "_icgan_bn", (None, None))
-        h = self.bn1.fused(x, y, relu=True, up=up, sums=pre[0], shift=pre[1])
-        s1 = self.conv1.bn_stats_buffer(h)
-        h = self.conv1.conv_nhwc(h, stats=s1)
+        sub = (up and ops.SUBPIXEL_UP and x.dtype == torch.bfloat16 and self.conv1.in_channels % 16 == 0
+               and self.conv1.out_channels % 16 == 0)
+        if sub and not getattr(self.conv1, "sub_pixel_up", False):
+            self.conv1.sub_pixel_up = True
+            self.conv1._sn.version = None  # operand copies must be rebuilt with the merged slices
+        h = self.bn1.fused(x, y, relu=True, up=(up and not sub), sums=pre[0], shift=pre[1])
+        s1 = None if sub else self.conv1.bn_stats_buffer(h)
+        h = self.conv1.upconv_nhwc(h) if sub else self.conv1.conv_nhwc(h, stats=s1)
         h = self.bn2.fused(h, y, relu=True, up=False, sums=s1, shift=self.conv1.bias if s1 is not None else None)
         sc = self.conv_sc.conv_nhwc(x) if self.learnable_sc else x
         s2 = self.conv2.bn_stats_buffer(h)

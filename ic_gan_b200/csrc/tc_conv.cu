@@ -1556,7 +1556,8 @@ static void choose_tile(int Wd, int Hd, int B, int pixels, int max_w, int* TW, i
     }
 }
 
-extern "C" int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* bias, const void* residual, void* y, int B,
+extern "C" int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* alpha_dev, const float* bias,
+                                  const void* residual, void* y, int B,
                                   int H, int W, int Cin, int Cout, int wtaps, int ntaps, const int* tap_dh,
                                   const int* tap_dw, const int* tap_w, int in_stride, int Hd, int Wd, int OH, int OW,
                                   int osy, int ooy, int osx, int oox, int out_dtype, int res_dtype, void* stream) {
@@ -1614,7 +1615,7 @@ extern "C" int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* bi
   p.res_bf16 = res_dtype == ICGAN_BF16;
   p.res_shift = 0;
   p.act = ICGAN_ACT_NONE;
-  p.y = y; p.bias = bias; p.res = residual; p.alpha = nullptr; p.stats = nullptr;
+  p.y = y; p.bias = bias; p.res = residual; p.alpha = alpha_dev; p.stats = nullptr;
 
   CUtensorMap tmA, tmB;
   {

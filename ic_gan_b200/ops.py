@@ -163,6 +163,11 @@ class SNState:
             return
         self.version = stamp
         co, ci, k, _ = w.shape
+        if getattr(self.module, "sub_pixel_up", False) and k == 3:  # merged 2x2-phase slices of the sub-pixel up-conv
+            w9 = w.detach().permute(0, 2, 3, 1).reshape(co, 9, ci)
+            up = torch.einsum("tk,okc->otc", up_merge_matrix(w.device), w9)
+            self.wk_up = up.to(torch.bfloat16).contiguous()                      # [Co, 16, Ci]
+            self.wk_up_d = up.permute(2, 1, 0).to(torch.bfloat16).contiguous()   # [Ci, 16, Co]
         if self.co_pad:  # zero-padded output channels: relayout in float32, pad, narrow (small 1x1 weights only)
             f32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32)
             d32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32)
@@ -400,6 +405,100 @@ class SNConvFn(torch.autograd.Function):
                          stream_ptr())
             dW = st.weight_grad(G, ctx.snap)
         return dx, dW, db, dres, None, None, None, None, None, None, None
+
+
+# ===================================================================================== sub-pixel up-convolution
+# conv3x3(nearest_up2(x)) -- every GBlock's conv1 (BigGAN.py:256-262, layers.py:542-546) -- without the upsampled tensor:
+# output pixel (2i+a, 2j+b) only ever sees the 2x2 low-resolution neighbourhood of (i, j), so each of the four output
+# parity classes is a 2x2-tap convolution of x with kernel rows / columns of the 3x3 filter merged:
+#   a = 0: source rows (i-1, i) with (w[0], w[1]+w[2]);   a = 1: source rows (i, i+1) with (w[0]+w[1], w[2])
+# 16 MACs per low-resolution pixel instead of 36, no [B,2H,2W,C] operand written by the batch norm or read by the conv.
+# All three products run on the tap-table tensor-core kernels (icgan_conv2d_tc_ex / icgan_conv2d_wgrad_tc_ex).
+SUBPIXEL_UP = bool(int(__import__("os").environ.get("ICGAN_SUBPIXEL_UP", "0")))
+_UP_SRC = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}  # parity -> ((source offset, merged kernel rows), ...)
+
+
+def _up_slices():
+    """[(a, b, dh, dw, rows, cols)] for the 16 merged weight slices, index t = ((a*2+b)*2+u)*2+v."""
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            for dh, rows in _UP_SRC[a]:
+                for dw, cols in _UP_SRC[b]:
+                    out.append((a, b, dh, dw, rows, cols))
+    return out
+
+
+_UP_SLICES = _up_slices()
+
+
+def up_merge_matrix(device):
+    """M[t, kh*3+kw] = 1 where 3x3 tap (kh, kw) is merged into slice t (float32 [16, 9])."""
+    M = torch.zeros(16, 9)
+    for t, (_, _, _, _, rows, cols) in enumerate(_UP_SLICES):
+        for kh in rows:
+            for kw in cols:
+                M[t, kh * 3 + kw] = 1.0
+    return M.to(device)
+
+
+class UpConvFn(torch.autograd.Function):
+    """y[B,2H,2W,Co] = conv3x3(nearest_up2(x), W/sigma) + bias, x [B,H,W,Ci] bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, st: "SNState"):
+        x = x.contiguous()
+        B, H, W, ci = x.shape
+        co = weight.shape[0]
+        y = torch.empty(B, 2 * H, 2 * W, co, device=x.device, dtype=x.dtype)
+        for a in (0, 1):
+            for b in (0, 1):
+                taps = [(dh, dw, t) for t, (pa, pb, dh, dw, _, _) in enumerate(_UP_SLICES) if (pa, pb) == (a, b)]
+                _SHAPE[0] = ("up", B, H, W, ci, co, a, b)
+                _timed("tc_conv_kernel", 2.0 * B * H * W * co * ci * 4, lambda: call(
+                    "icgan_conv2d_tc_ex", ptr(x), ptr(st.wk_up), ptr(st.alpha), ptr(bias), None, ptr(y), B, H, W, ci, co, 16, 4,
+                    L.int_array([t[0] for t in taps]), L.int_array([t[1] for t in taps]), L.int_array([t[2] for t in taps]),
+                    1, H, W, 2 * H, 2 * W, 2, a, 2, b, dt(y), L.F32, stream_ptr()))
+        ctx.st, ctx.snap, ctx.has_bias = st, st.snap, bias is not None
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        st: SNState = ctx.st
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        B, H, W, ci = x.shape
+        co = dy.shape[3]
+        dx = dW = db = None
+        # the adjoint reads dy at (2i + a - 2dh, 2j + b - 2dw): one stride-2 launch with all 16 merged slices
+        offs = [(a - 2 * dh, b - 2 * dw) for (a, b, dh, dw, _, _) in _UP_SLICES]
+        alpha = ctx.snap[2][1:] if st.use_sn else None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, H, W, ci, device=x.device, dtype=x.dtype)
+            _SHAPE[0] = ("up_dgrad", B, H, W, co, ci)
+            _timed("tc_conv_kernel", 2.0 * B * H * W * co * ci * 16, lambda: call(
+                "icgan_conv2d_tc_ex", ptr(dy), ptr(st.wk_up_d), ptr(alpha), None, None, ptr(dx), B, 2 * H, 2 * W, co, ci, 16, 16,
+                L.int_array([o[0] for o in offs]), L.int_array([o[1] for o in offs]), L.int_array(list(range(16))),
+                2, H, W, H, W, 1, 0, 1, 0, dt(dx), L.F32, stream_ptr()))
+        if ctx.needs_input_grad[1]:
+            G16 = torch.zeros(4, ci, 4, co, device=x.device, dtype=torch.float32)  # [phase][ci][slice in phase][co]
+            for ph in range(4):
+                o4 = offs[4 * ph:4 * ph + 4]
+                _SHAPE[0] = ("up_wgrad", B, H, W, ci, co, ph)
+                _timed("tc_wgrad_kernel", 2.0 * B * H * W * co * ci * 4, lambda: call(
+                    "icgan_conv2d_wgrad_tc_ex", ptr(x), ptr(dy), ptr(G16[ph]), B, H, W, ci, 2 * H, 2 * W, co, 4,
+                    L.int_array([o[0] for o in o4]), L.int_array([o[1] for o in o4]), 2, stream_ptr()))
+            # un-merge: dW[co, kh, kw, ci] = sum of the slices that contain tap (kh, kw)
+            M = up_merge_matrix(x.device)
+            G9 = torch.einsum("tk,itc->ikc", M, G16.permute(1, 0, 2, 3).reshape(ci, 16, co))
+            dW = st.weight_grad(G9.permute(2, 1, 0).reshape(co, 3, 3, ci).contiguous(), ctx.snap)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(co, device=dy.device, dtype=torch.float32)
+            call("icgan_channel_sum", ptr(dy), ptr(db), B * 4 * H * W, co, dt(dy), stream_ptr())
+        return dx, dW, db, None
 
 
 # ===================================================================================== linear / embedding
