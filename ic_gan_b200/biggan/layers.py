@@ -94,6 +94,9 @@ class SNConv2d(nn.Conv2d, SN):
     def upconv_nhwc(self, x):
         """conv3x3(nearest_up2(x)) in sub-pixel form (ops.UpConvFn): x is the LOW-resolution tensor."""
         st = self._sn_ready()
+        if getattr(st, "up_version", None) != (self.weight._version, ops._WEIGHT_EPOCH[0]):
+            with torch.no_grad():
+                st.build_up_operands()  # first use, or the weights changed since the slices were merged
         return ops.UpConvFn.apply(x, self.weight, self.bias, st)
 
     def bn_stats_buffer(self, x):
@@ -244,9 +247,8 @@ class GBlock(nn.Module):
         pre = getattr(x, "_icgan_bn", (None, None))
         sub = (up and ops.SUBPIXEL_UP and x.dtype == torch.bfloat16 and self.conv1.in_channels % 16 == 0
                and self.conv1.out_channels % 16 == 0)
-        if sub and not getattr(self.conv1, "sub_pixel_up", False):
-            self.conv1.sub_pixel_up = True
-            self.conv1._sn.version = None  # operand copies must be rebuilt with the merged slices
+        if sub:
+            self.conv1.sub_pixel_up = True  # refresh_sn then re-merges the slices whenever the weights change
         h = self.bn1.fused(x, y, relu=True, up=(up and not sub), sums=pre[0], shift=pre[1])
         s1 = None if sub else self.conv1.bn_stats_buffer(h)
         h = self.conv1.upconv_nhwc(h) if sub else self.conv1.conv_nhwc(h, stats=s1)

@@ -163,11 +163,8 @@ class SNState:
             return
         self.version = stamp
         co, ci, k, _ = w.shape
-        if getattr(self.module, "sub_pixel_up", False) and k == 3:  # merged 2x2-phase slices of the sub-pixel up-conv
-            w9 = w.detach().permute(0, 2, 3, 1).reshape(co, 9, ci)
-            up = torch.einsum("tk,okc->otc", up_merge_matrix(w.device), w9)
-            self.wk_up = up.to(torch.bfloat16).contiguous()                      # [Co, 16, Ci]
-            self.wk_up_d = up.permute(2, 1, 0).to(torch.bfloat16).contiguous()   # [Ci, 16, Co]
+        if getattr(self.module, "sub_pixel_up", False) and k == 3:
+            self.build_up_operands()
         if self.co_pad:  # zero-padded output channels: relayout in float32, pad, narrow (small 1x1 weights only)
             f32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32)
             d32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32)
@@ -186,6 +183,16 @@ class SNState:
         call("icgan_sn_prepare_weight", ptr(w), None, ptr(f32), ptr(d32), co, ci, k, L.F32, stream_ptr())
         self.wk_fwd = self._operand(f32, self.mode, self.kp)
         self.wk_dgrad = self._operand(d32, self.mode_d, self.kp_d)
+
+    def build_up_operands(self):
+        """Merged 2x2-phase slices of the sub-pixel up-convolution (UpConvFn), from the float32 master weight."""
+        w = self.module.weight
+        co, ci, k, _ = w.shape
+        w9 = w.detach().permute(0, 2, 3, 1).reshape(co, 9, ci)
+        up = torch.einsum("tk,okc->otc", up_merge_matrix(w.device), w9)
+        self.wk_up = up.to(torch.bfloat16).contiguous()                      # [Co, 16, Ci]
+        self.wk_up_d = up.permute(2, 1, 0).to(torch.bfloat16).contiguous()   # [Ci, 16, Co]
+        self.up_version = (w._version, _WEIGHT_EPOCH[0])
 
     def weight_grad(self, G: Tensor, snap=None) -> Tensor:
         """dL/dW (master layout) from G = dL/d(W/sigma) given in operand layout (float32); `snap` = the (v, u', sigma)

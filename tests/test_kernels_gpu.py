@@ -267,5 +267,5 @@ def test_subpixel_upconv_matches_upsample_then_conv(cuda_device):
     rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-20))
     assert rel(o1, o0) <= 2e-2 and rel(dx1, dx0) <= 3e-2, (rel(o1, o0), rel(dx1, dx0))
     for k in g0:
-        if g0[k].abs().max() > 1e-4:
+        if g0[k].abs().max() > 1e-4 and k != "conv1.bias":  # conv1.bias feeds bn2: analytically zero, rounding noise only
             assert rel(g1[k], g0[k]) <= 5e-2, (k, rel(g1[k], g0[k]))
