@@ -33,7 +33,7 @@ class IcganSnLayer(C.Structure):
 SIGNATURES = {
     "icgan_conv2d_tc": [vp, vp, fp, fp, vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_tc_ex": [vp, vp, fp, fp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
-                           i32, i32, i32, i32, vp],
+                           i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_tc_ex": [vp, vp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
     "icgan_conv2d_rgb_tc": [vp, vp, fp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "icgan_conv2d_wgrad_tc": [vp, vp, fp, i32, i32, i32, i32, i32, i32, vp],

@@ -99,6 +99,14 @@ class SNConv2d(nn.Conv2d, SN):
                 st.build_up_operands()  # first use, or the weights changed since the slices were merged
         return ops.UpConvFn.apply(x, self.weight, self.bias, st)
 
+    def downconv_nhwc(self, x, residual=None, mask_input=False):
+        """avgpool2(conv3x3(x)) + residual as one stride-2 4x4 convolution (ops.DownConvFn)."""
+        st = self._sn_ready()
+        if getattr(st, "down_version", None) != (self.weight._version, ops._WEIGHT_EPOCH[0]):
+            with torch.no_grad():
+                st.build_down_operands()
+        return ops.DownConvFn.apply(x, self.weight, self.bias, residual, st, mask_input)
+
     def bn_stats_buffer(self, x):
         """float32 [2*Cout] accumulator if this conv can emit the batch statistics of its output from its epilogue
         (tensor-core path, training, Cout % 32 == 0), else None."""
@@ -295,6 +303,10 @@ class DBlock(nn.Module):
         if self.learnable_sc:
             s = self.conv_sc.conv_nhwc(s)
         if down:
+            if (ops.POOLED_DOWN and h.dtype == torch.bfloat16 and self.conv2.in_channels % 16 == 0
+                    and self.conv2.out_channels % 8 == 0 and h.shape[1] % 2 == 0 and h.shape[2] % 2 == 0):
+                self.conv2.pooled_down = True
+                return self.conv2.downconv_nhwc(h, residual=s, mask_input=True)
             h = self.conv2.conv_nhwc(h, mask_input=True)
             return ops.Pool2Fn.apply(h, s, 0.25, 0)
         return self.conv2.conv_nhwc(h, residual=s, mask_input=True)

@@ -1560,8 +1560,10 @@ extern "C" int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* al
                                   const void* residual, void* y, int B,
                                   int H, int W, int Cin, int Cout, int wtaps, int ntaps, const int* tap_dh,
                                   const int* tap_dw, const int* tap_w, int in_stride, int Hd, int Wd, int OH, int OW,
-                                  int osy, int ooy, int osx, int oox, int out_dtype, int res_dtype, void* stream) {
+                                  int osy, int ooy, int osx, int oox, int out_dtype, int res_dtype, int res_mask,
+                                  void* stream) {
   ICGAN_REQUIRE(x && wk && y && tap_dh && tap_dw && tap_w, "icgan_conv2d_tc_ex: null pointer");
+  ICGAN_REQUIRE(!res_mask || residual, "icgan_conv2d_tc_ex: res_mask needs a mask tensor");
   ICGAN_REQUIRE(ntaps >= 1 && ntaps <= 16 && wtaps >= 1 && wtaps <= 127, "icgan_conv2d_tc_ex: 1..16 taps (got %d)", ntaps);
   ICGAN_REQUIRE(in_stride == 1 || in_stride == 2, "icgan_conv2d_tc_ex: input stride 1 or 2 (got %d)", in_stride);
   ICGAN_REQUIRE(B > 0 && H > 0 && W > 0 && Hd > 0 && Wd > 0 && OH > 0 && OW > 0, "icgan_conv2d_tc_ex: bad shape");
@@ -1613,7 +1615,7 @@ extern "C" int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* al
   p.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.BN));
   p.out_bf16 = out_dtype == ICGAN_BF16;
   p.res_bf16 = res_dtype == ICGAN_BF16;
-  p.res_shift = 0;
+  p.res_shift = res_mask ? 2 : 0;  // 2: `residual` gates the result (y = residual > 0 ? y : 0) instead of being added
   p.act = ICGAN_ACT_NONE;
   p.y = y; p.bias = bias; p.res = residual; p.alpha = alpha_dev; p.stats = nullptr;
 

@@ -108,7 +108,7 @@ def _launch_ex(x, wk, y, res, taps, in_stride, dom, omap):
         "icgan_conv2d_tc_ex", ptr(x), ptr(wk), None, None, ptr(res), ptr(y), B, H, W, ci, co, wt, len(taps),
         int_array([t[0] for t in taps]), int_array([t[1] for t in taps]), int_array([t[2] for t in taps]), in_stride,
         dom[0], dom[1], y.shape[1], y.shape[2], omap[0], omap[1], omap[2], omap[3], dt(y),
-        dt(res) if res is not None else L.F32, stream_ptr()))
+        dt(res) if res is not None else L.F32, 0, stream_ptr()))
 
 
 def _run_tc(x, wk32, launch, out_shape):

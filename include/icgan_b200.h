@@ -76,13 +76,14 @@ int icgan_conv2d_wgrad_tc(const void* x, const void* dy, float* dwk, int B, int 
  *     y[n, h*osy+ooy, w*osx+oox, co] = alpha * sum_t sum_ci x[n, h*in_stride+tap_dh[t], w*in_stride+tap_dw[t], ci] * wk[co, tap_w[t], ci]
  *                                      + bias[co] + residual[n, h*osy+ooy, w*osx+oox, co]     (alpha_dev: device scalar or NULL = 1)
  * x: [B,H,W,Cin] bf16 (reads outside the tensor are zero), wk: [Cout, wtaps, Cin] bf16, y/residual: [B,OH,OW,Cout];
+ * res_mask = 1: `residual` is not added but gates the result (y = residual > 0 ? y : 0: a ReLU backward fused into a dgrad).
  * tap_* are HOST int arrays of ntaps (<= 16) entries. A stride-2 convolution is one call (in_stride=2); a stride-2
  * transposed convolution is four calls, one per output parity class (osy=osx=2, oo* = parity), each with the 1, 2 or 4
  * taps that reach that class. */
 int icgan_conv2d_tc_ex(const void* x, const void* wk, const float* alpha_dev, const float* bias, const void* residual,
                        void* y, int B, int H, int W, int Cin, int Cout, int wtaps, int ntaps, const int* tap_dh_host, const int* tap_dw_host,
                        const int* tap_w_host, int in_stride, int Hd, int Wd, int OH, int OW, int osy, int ooy, int osx,
-                       int oox, int out_dtype, int res_dtype, void* stream);
+                       int oox, int out_dtype, int res_dtype, int res_mask, void* stream);
 /* Weight gradient of the same family (replaces cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight,
  * conv2d_gradfix.py:223-227):  out[ca, t, cb] += sum_{n,h,w} a[n,h,w,ca] * b[n, h*in_stride+tap_dh[t], w*in_stride+tap_dw[t], cb]
  * a: [B,Ha,Wa,Ca] bf16, b: [B,Hb,Wb,Cb] bf16 (zero outside), out: float32 [Ca, ntaps, Cb], ACCUMULATED. Cb%16==0, Ca%8==0. */

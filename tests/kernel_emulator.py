@@ -157,8 +157,8 @@ def _conv_ex(xv, wk, taps_dh, taps_dw, taps_w, in_stride, Hd, Wd):
 
 
 def icgan_conv2d_tc_ex(x, wk, alpha, bias, res, y, B, H, W, Ci, Co, wt, nt, tdh, tdw, tw, in_stride, Hd, Wd, OH, OW, osy, ooy, osx,
-                       oox, out_dt, res_dt, stream):
-    assert Ci % 16 == 0 and Co % 8 == 0 and nt <= 16 and alpha is None
+                       oox, out_dt, res_dt, res_mask, stream):
+    assert Ci % 16 == 0 and Co % 8 == 0 and nt <= 16 and alpha is None and not res_mask
     xv = _flat(x, torch.bfloat16)[:B * H * W * Ci].view(B, H, W, Ci).float()
     wv = _flat(wk, torch.bfloat16)[:Co * wt * Ci].view(Co, wt, Ci).float()
     val = _conv_ex(xv, wv, _ints(tdh)[:nt], _ints(tdw)[:nt], _ints(tw)[:nt], in_stride, Hd, Wd)
@@ -182,7 +182,7 @@ def icgan_conv2d_tc(x, wk, alpha, bias, res, y, stats, B, H, W, Ci, Co, k, out_d
     p = k // 2
     taps = [(kh - p, kw - p, kh * k + kw) for kh in range(k) for kw in range(k)]
     icgan_conv2d_tc_ex(x, wk, None, bias, res, y, B, H, W, Ci, Co, k * k, len(taps), [t[0] for t in taps], [t[1] for t in taps],
-                       [t[2] for t in taps], 1, H, W, H, W, 1, 0, 1, 0, out_dt, res_dt, stream)
+                       [t[2] for t in taps], 1, H, W, H, W, 1, 0, 1, 0, out_dt, res_dt, 0, stream)
 
 
 def icgan_conv2d_wgrad_tc_ex(a, b, out, B, Ha, Wa, Ca, Hb, Wb, Cb, nt, tdh, tdw, in_stride, stream):

@@ -269,3 +269,42 @@ def test_subpixel_upconv_matches_upsample_then_conv(cuda_device):
     for k in g0:
         if g0[k].abs().max() > 1e-4 and k != "conv1.bias":  # conv1.bias feeds bn2: analytically zero, rounding noise only
             assert rel(g1[k], g0[k]) <= 5e-2, (k, rel(g1[k], g0[k]))
+
+
+def test_pooled_downconv_matches_conv_then_pool(cuda_device):
+    """ops.DownConvFn (avgpool2(conv3x3(h)) + shortcut as one stride-2 4x4 convolution, 16 instead of 36 MACs per output pixel;
+    transposed parity classes with the ReLU gate for dgrad; tap-table wgrad) against the plain DBlock tail, bf16."""
+    import copy
+    import functools
+    from ic_gan_b200 import ops
+    from ic_gan_b200.biggan import layers
+    conv = functools.partial(layers.SNConv2d, kernel_size=3, padding=1, num_svs=1, num_itrs=1, eps=1e-8)
+    torch.manual_seed(5)
+    ref_blk = layers.DBlock(32, 64, which_conv=conv, wide=True, preactivation=True, activation=torch.nn.ReLU(),
+                            downsample=torch.nn.AvgPool2d(2)).to(cuda_device)
+    new_blk = copy.deepcopy(ref_blk)
+    for blk in (ref_blk, new_blk):
+        for m in blk.modules():
+            if isinstance(m, layers.SN):
+                m.compute_dtype = torch.bfloat16
+        blk.train()
+    g = torch.Generator(device=cuda_device).manual_seed(6)
+    x0 = torch.randn(3, 32, 32, 32, device=cuda_device, generator=g).bfloat16()
+    outs = []
+    old = ops.POOLED_DOWN
+    try:
+        for flag, blk in ((False, ref_blk), (True, new_blk)):
+            ops.POOLED_DOWN = flag
+            x = x0.clone().requires_grad_(True)
+            out = blk(x)
+            gy = torch.randn(out.shape, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(9))
+            out.float().backward(gy)
+            outs.append((out.float(), x.grad.float(), {k: p.grad.clone() for k, p in blk.named_parameters()}))
+    finally:
+        ops.POOLED_DOWN = old
+    assert getattr(new_blk.conv2, "pooled_down", False) and not getattr(ref_blk.conv2, "pooled_down", False)
+    (o0, dx0, g0), (o1, dx1, g1) = outs
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-20))
+    assert rel(o1, o0) <= 2e-2 and rel(dx1, dx0) <= 3e-2, (rel(o1, o0), rel(dx1, dx0))
+    for k in g0:
+        assert rel(g1[k], g0[k]) <= 5e-2, (k, rel(g1[k], g0[k]))
