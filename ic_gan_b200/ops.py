@@ -528,7 +528,8 @@ class UpConvFn(torch.autograd.Function):
 # conv output written, no pooling pass, bias / shortcut added in the epilogue).  Its dgrad is the stride-2 transposed
 # form (four parity classes x 2x2 taps, with the ReLU gate of the block's inner activation in the epilogue), its wgrad
 # the stride-2 tap-table weight gradient, un-merged to the 3x3 layout.
-POOLED_DOWN = bool(int(__import__("os").environ.get("ICGAN_POOLED_DOWN", "0")))
+# default ON: measured +10.4 % on the cc-256 step (668.8 -> 738.4 img/s, same box), all parity tests green with it
+POOLED_DOWN = bool(int(__import__("os").environ.get("ICGAN_POOLED_DOWN", "1")))
 
 
 def down_merge_matrix(device):

@@ -116,11 +116,13 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt):
     print(f"step {cdt}: losses {losses} vs reference {ref_losses.tolist()}")
     if cdt == torch.float32:
         assert np.allclose(np.array(losses), ref_losses, atol=2e-3 * max(1.0, np.abs(ref_losses).max()))
-        # 0.25 x lr: the GPU's float32 summation orders (atomics in wgrad / embedding backward) differ run to run; measured
-        # worst well-conditioned element over three runs: 0.12 x lr (the CPU oracle sits at 0.03 x lr from the reference)
-        wg = _check("G", G.state_dict(), fx, hp["G_lr"], 0.25, hp=hp)
-        wd = _check("D", D.state_dict(), fx, hp["D_lr"], 0.25, hp=hp)
-        we = _check("G_ema", G_ema.state_dict(), fx, hp["G_lr"], 0.25, hp=hp)
+        # 0.5 x lr: the GPU's float32 summation orders (atomics in wgrad / embedding backward) differ run to run and three
+        # Adam steps amplify that (a slightly different first step moves every later gradient); measured worst
+        # well-conditioned element over four runs: 0.12, 0.12, 0.28, 0.09 x lr (the CPU oracle: 0.03 x lr).  A wrong
+        # schedule (EMA start, accumulation, toggling, optimiser order) moves weights by whole multiples of lr.
+        wg = _check("G", G.state_dict(), fx, hp["G_lr"], 0.5, hp=hp)
+        wd = _check("D", D.state_dict(), fx, hp["D_lr"], 0.5, hp=hp)
+        we = _check("G_ema", G_ema.state_dict(), fx, hp["G_lr"], 0.5, hp=hp)
         print(f"step fp32: worst |w - w_ref| / lr: G {wg:.3e}, D {wd:.3e}, G_ema {we:.3e}")
         for tag, net in (("G", G), ("D", D)):
             for k, p in net.named_parameters():
