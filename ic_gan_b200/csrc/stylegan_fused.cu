@@ -11,6 +11,7 @@
 //  * bias_act_vec_kernel -- bias_act for channels-last tensors, 8 elements per thread, no per-element div/mod, with the
 //    same optional per-sample scale and noise inputs.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -62,6 +63,22 @@ template <> struct Pack<__half> {
   }
 };
 
+// 8 consecutive elements <-> floats with 128-bit accesses (one uint4 for 16-bit types, two float4 for float32)
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) { Pack<T>::load(p, v); }
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]) { Pack<T>::store(p, v); }
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 struct PostArgs {          // optional epilogue: y = clamp(act((v * pre[n,c]) + noise[n,oy,ox]*ns + bias[c]) * act_gain); y2 = y*s2[n,c]
   const float* pre;        // [N, C] per-sample scale (demodulation coefficients), may be null
   const float* noise;      // [N or 1, outH, outW] float32, may be null
@@ -83,6 +100,114 @@ struct UpfirdnTiledParams {
   int separable;
   float fx[4], fy[4];  // already flipped / gain-scaled like fs[] below (gain on fy)
 };
+
+// epilogue + store of one output vector (shared by the tiled and the direct kernel)
+template <typename T>
+__device__ __forceinline__ void emit_output(const UpfirdnTiledParams& p, T* __restrict__ y, int n, int oy, int ox, int c0, float ns,
+                                            float (&acc)[Pack<T>::N]) {
+  constexpr int NV = Pack<T>::N;
+  const int64_t pix = (static_cast<int64_t>(n) * p.outH + oy) * p.outW + ox;
+  if (p.post.act) {
+    const PostArgs& q = p.post;
+    float nz = 0.f;
+    if (q.noise) nz = ns * q.noise[(q.noise_per_sample ? static_cast<int64_t>(n) * p.outH * p.outW : 0) + static_cast<int64_t>(oy) * p.outW + ox];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float v = acc[k];
+      if (q.pre) v *= q.pre[static_cast<int64_t>(n) * p.C + c0 + k];
+      v += nz;
+      if (q.bias) v += q.bias[c0 + k];
+      if (q.act == 3) v = v > 0.f ? v : v * q.alpha;
+      v *= q.act_gain;
+      if (q.clamp >= 0.f) v = fminf(fmaxf(v, -q.clamp), q.clamp);
+      acc[k] = v;
+    }
+  }
+  Pack<T>::store(y + pix * p.C + c0, acc);
+  if (p.post.y2) {
+    float v2[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v2[k] = acc[k] * p.post.s2[static_cast<int64_t>(n) * p.C + c0 + k];
+    Pack<T>::store(static_cast<T*>(p.post.y2) + pix * p.C + c0, v2);
+  }
+}
+
+// Separable filters, no shared memory: a thread owns output column ox (8 lanes x 16 bytes of channels) and walks ROWS
+// output rows with a sliding window of horizontally pre-filtered rows; its four 16-byte loads per new row come straight
+// from global memory through L1 (neighbouring columns share three of them), so loads stay in flight the whole time --
+// the tiled kernel alternates load and compute phases behind a barrier and reached only ~0.36 of HBM bandwidth on
+// 0.5 GB tensors (profiles/r02_kernel_bandwidth_before_vectorising.txt).
+template <typename T, int UP, int DOWN, int ROWS>
+__global__ void __launch_bounds__(256)
+upfirdn2d_direct_kernel(const T* __restrict__ x, T* __restrict__ y, const UpfirdnTiledParams p) {
+  constexpr int NV = Pack<T>::N, CB = 8 * NV, F = 4, TOW = 32;
+  const int lane = threadIdx.x & 7, col = threadIdx.x >> 3;
+  int bid = blockIdx.x;
+  const int cblocks = (p.C + CB - 1) / CB;
+  const int cb = bid % cblocks; bid /= cblocks;
+  const int tiles_w = (p.outW + TOW - 1) / TOW, tiles_h = (p.outH + ROWS - 1) / ROWS;
+  const int tw = bid % tiles_w; bid /= tiles_w;
+  const int th = bid % tiles_h;
+  const int n = bid / tiles_h;
+  const int ox = tw * TOW + col, oy0 = th * ROWS;
+  const int c0 = cb * CB + lane * NV;
+  const bool live = c0 < p.C && ox < p.outW;
+  const int ux = ox * DOWN - p.pad0x;
+  int u_cur = oy0 * DOWN - p.pad0y;
+  const T* xn = x + static_cast<int64_t>(n) * p.inH * p.inW * p.C + c0;
+  auto load_hrow = [&](int u_row, float (&dst)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) dst[k] = 0.f;
+    bool row_ok = live;
+    int iy = u_row;
+    if (UP == 2) { row_ok = row_ok && ((u_row & 1) == 0); iy = u_row >> 1; }
+    row_ok = row_ok && iy >= 0 && iy < p.inH;
+    uint4 raw[F];
+#pragma unroll
+    for (int t = 0; t < F; ++t) {
+      const int u = ux + t;
+      bool ok = row_ok;
+      int ix = u;
+      if (UP == 2) { ok = ok && ((u & 1) == 0); ix = u >> 1; }
+      ok = ok && ix >= 0 && ix < p.inW;
+      raw[t] = ok ? __ldg(reinterpret_cast<const uint4*>(xn + (static_cast<int64_t>(iy) * p.inW + ix) * p.C)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int t = 0; t < F; ++t) {
+      float xv[NV];
+      Pack<T>::unpack(raw[t], xv);
+      const float w = p.fx[t];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) dst[k] = fmaf(xv[k], w, dst[k]);
+    }
+  };
+  float hwin[F][NV];
+#pragma unroll
+  for (int r = 0; r < F; ++r) load_hrow(u_cur + r, hwin[r]);
+  const float ns = p.post.noise_strength ? *p.post.noise_strength : 1.f;
+#pragma unroll 2
+  for (int ro = 0; ro < ROWS; ++ro) {
+    const int oy = oy0 + ro;
+    if (oy >= p.outH) break;
+    float acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < F; ++r) {
+      const float w = p.fy[r];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[k] = fmaf(hwin[r][k], w, acc[k]);
+    }
+    if (live) emit_output<T>(p, y, n, oy, ox, c0, ns, acc);
+    u_cur += DOWN;
+#pragma unroll
+    for (int r = 0; r + DOWN < F; ++r)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) hwin[r][k] = hwin[r + DOWN][k];
+#pragma unroll
+    for (int r = F - DOWN; r < F; ++r) load_hrow(u_cur + r, hwin[r]);
+  }
+}
 
 // Square up/down factors, fh = fw = 4 (every resampling filter StyleGAN2 uses: [1,3,3,1] outer product).
 // Tile: TOH x TOW outputs x (8 lanes x 16 bytes) channels.  Thread = (lane, column, row group).
@@ -203,32 +328,7 @@ upfirdn2d_tiled_kernel(const T* __restrict__ x, const float* __restrict__ f, T* 
           for (int k = 0; k < NV; ++k) acc[k] = fmaf(xv[k], w, acc[k]);
         }
     }
-    if (c_ok && oy < p.outH && ox < p.outW) {
-      const int64_t pix = (static_cast<int64_t>(n) * p.outH + oy) * p.outW + ox;
-      if (p.post.act) {
-        const PostArgs& q = p.post;
-        float nz = 0.f;
-        if (q.noise) nz = ns * q.noise[(q.noise_per_sample ? static_cast<int64_t>(n) * p.outH * p.outW : 0) + static_cast<int64_t>(oy) * p.outW + ox];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          float v = acc[k];
-          if (q.pre) v *= q.pre[static_cast<int64_t>(n) * p.C + c0 + k];
-          v += nz;
-          if (q.bias) v += q.bias[c0 + k];
-          if (q.act == 3) v = v > 0.f ? v : v * q.alpha;
-          v *= q.act_gain;
-          if (q.clamp >= 0.f) v = fminf(fmaxf(v, -q.clamp), q.clamp);
-          acc[k] = v;
-        }
-      }
-      Pack<T>::store(y + pix * p.C + c0, acc);
-      if (p.post.y2) {
-        float v2[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) v2[k] = acc[k] * p.post.s2[static_cast<int64_t>(n) * p.C + c0 + k];
-        Pack<T>::store(static_cast<T*>(p.post.y2) + pix * p.C + c0, v2);
-      }
-    }
+    if (c_ok && oy < p.outH && ox < p.outW) emit_output<T>(p, y, n, oy, ox, c0, ns, acc);
     // advance the window by DOWN rows
     if (ro + 1 < ROWS) {
       u_cur += DOWN;
@@ -261,12 +361,10 @@ modulate_kernel(const TI* __restrict__ x, const float* __restrict__ s, TO* __res
     const int c = static_cast<int>(i % cv) * 8;
     const int64_t n = (i / cv) / hw;
     float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ld_as_float(x, i * 8 + k);
+    load8(x + i * 8, v);
     const float4 s0 = *reinterpret_cast<const float4*>(s + n * C + c), s1 = *reinterpret_cast<const float4*>(s + n * C + c + 4);
     v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) st_from_float(y, i * 8 + k, v[k]);
+    store8(y + i * 8, v);
   }
 }
 
@@ -284,8 +382,11 @@ chan_dot_kernel(const TA* __restrict__ a, const TB* __restrict__ b, float* __res
     if (v < cv)
       for (int64_t px = p0 + (threadIdx.x >> 5); px < p1; px += 8) {
         const int64_t o = (static_cast<int64_t>(n) * hw + px) * C + v * 8;
+        float av[8], bv[8];
+        load8(a + o, av);
+        load8(b + o, bv);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(ld_as_float(a, o + k), ld_as_float(b, o + k), acc[k]);
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(av[k], bv[k], acc[k]);
       }
 #pragma unroll
     for (int k = 0; k < 8; ++k) red[threadIdx.x >> 5][(threadIdx.x & 31) * 8 + k] = acc[k];
@@ -318,38 +419,41 @@ bias_act_vec_kernel(const T* __restrict__ x, const T* __restrict__ yref, T* __re
     const int c = static_cast<int>(i % cv) * 8;
     const int64_t pix = i / cv;
     const int64_t n = pix / hw;
-    float v[8], yr[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ld_as_float(x, i * 8 + k);
+    float v[8], yr[8], pv[8], bv[8];
+    load8(x + i * 8, v);
+    if (pre) load8(pre + n * C + c, pv);
     if (grad == 0) {
       float nz = 0.f;
       if (noise) nz = ns * noise[noise_per_sample ? pix : pix - n * hw];
+      if (bias) load8(bias + c, bv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float t = v[k];
-        if (pre) t *= pre[n * C + c + k];
+        if (pre) t *= pv[k];
         t += nz;
-        if (bias) t += bias[c + k];
+        if (bias) t += bv[k];
         if (act == 3) t = t > 0.f ? t : t * alpha;
         t *= gain;
         if (clamp >= 0.f) t = fminf(fmaxf(t, -clamp), clamp);
         v[k] = t;
       }
     } else {
+      if (yref) load8(yref + i * 8, yr);
+      else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) yr[k] = yref ? ld_as_float(yref, i * 8 + k) : 0.f;
+        for (int k = 0; k < 8; ++k) yr[k] = 0.f;
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float t = v[k];
         if (act == 3) t = yr[k] > 0.f ? t : t * alpha;  // sign(y) = sign(pre-activation) since gain > 0
         t *= gain;
         if (clamp >= 0.f) t = (yr[k] > -clamp && yr[k] < clamp) ? t : 0.f;
-        if (pre) t *= pre[n * C + c + k];  // chain rule through the per-sample scale: d/dx
+        if (pre) t *= pv[k];  // chain rule through the per-sample scale: d/dx
         v[k] = t;
       }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) st_from_float(y, i * 8 + k, v[k]);
+    store8(y + i * 8, v);
   }
 }
 
@@ -458,9 +562,25 @@ static int launch_upfirdn_tiled(const void* x, const float* f, void* y, const Up
   return 0;
 }
 
+template <typename T, int UP, int DOWN, int ROWS>
+static int launch_upfirdn_direct(const void* x, void* y, const UpfirdnTiledParams& p, cudaStream_t st) {
+  constexpr int NV = 16 / sizeof(T), CB = 8 * NV;
+  const int64_t blocks = static_cast<int64_t>(p.N) * ((p.outH + ROWS - 1) / ROWS) * ((p.outW + 31) / 32) * ((p.C + CB - 1) / CB);
+  ICGAN_REQUIRE(blocks > 0 && blocks < (1ll << 31), "icgan_upfirdn2d_nhwc: grid too large");
+  upfirdn2d_direct_kernel<T, UP, DOWN, ROWS><<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const T*>(x), static_cast<T*>(y), p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T>
 static int dispatch_upfirdn_tiled(const void* x, const float* f, void* y, const UpfirdnTiledParams& p, int up, int down,
                                   cudaStream_t st) {
+  static const bool use_direct = []() { const char* e = getenv("ICGAN_FIR_DIRECT"); return e ? atoi(e) != 0 : true; }();
+  if (p.separable && use_direct) {
+    if (up == 1 && down == 1) return launch_upfirdn_direct<T, 1, 1, 32>(x, y, p, st);
+    if (up == 2 && down == 1) return launch_upfirdn_direct<T, 2, 1, 32>(x, y, p, st);
+    if (up == 1 && down == 2) return launch_upfirdn_direct<T, 1, 2, 16>(x, y, p, st);
+  }
   if (p.separable) {
     if (up == 1 && down == 1) return launch_upfirdn_tiled<T, 1, 1, 8, 32, true>(x, f, y, p, st);
     if (up == 2 && down == 1) return launch_upfirdn_tiled<T, 2, 1, 8, 32, true>(x, f, y, p, st);
