@@ -63,6 +63,19 @@ def cpu_leg(flag, timeout_s=240):
         return None
 
 
+def nccl_to_stderr():
+    """NCCL's communicator lines ("... nranks N ...") are evidence the driver reads: make sure they are emitted (INFO
+    unless the caller asked for more) and send them to stderr -- fd 1 is pointed at stderr for the whole run and the one
+    JSON line is written to the saved original stdout."""
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = os.environ.get("ICGAN_NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    sys.stdout.flush()
+    JSON_OUT[0] = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def emit(line):
     out = JSON_OUT[0] or sys.stdout
     print(json.dumps(line), file=out, flush=True)
@@ -273,12 +286,7 @@ def run_knn(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("ICGAN_NCCL_DEBUG", "INFO"))
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        sys.stdout.flush()
-        JSON_OUT[0] = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
+        nccl_to_stderr()
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     gen = torch.Generator(device=dev).manual_seed(6)  # same table on every rank (replicated database)
@@ -487,12 +495,7 @@ def run_sg256(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("ICGAN_NCCL_DEBUG", "INFO"))
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        sys.stdout.flush()
-        JSON_OUT[0] = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
+        nccl_to_stderr()
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     torch.manual_seed(4321)
@@ -756,14 +759,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's communicator lines ("... nranks N ...") are evidence the driver reads; they go to stderr, stdout carries
-        # exactly one JSON line: fd 1 is pointed at stderr for the whole run and the JSON is written to the saved fd.
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("ICGAN_NCCL_DEBUG", "INFO"))
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        sys.stdout.flush()
-        JSON_OUT[0] = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
+        nccl_to_stderr()
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
