@@ -457,6 +457,104 @@ bias_act_vec_kernel(const T* __restrict__ x, const T* __restrict__ yref, T* __re
   }
 }
 
+// bias_act / demodulation epilogue with the per-sample and per-channel parameters resident in registers: a thread owns one
+// 8-channel vector of one sample and walks pixels (grid = (pixel slabs, N), 256 threads = 256/cv pixel rows x cv vectors).
+// The flat kernel above re-loads pre[n,c..c+8) and bias[c..c+8) per element vector -- 64 bytes of L1 requests next to 16
+// bytes of payload, which capped it at 0.46 of the HBM peak on 0.5 GB tensors (profiles/r02_kernel_bandwidth.txt).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_slab_kernel(const T* __restrict__ x, const T* __restrict__ yref, T* __restrict__ y, const float* __restrict__ bias,
+                     const float* __restrict__ pre, const float* __restrict__ noise, const float* __restrict__ noise_strength,
+                     int noise_per_sample, int64_t hw, int C, int slab, int grad, int act, float alpha, float gain, float clamp) {
+  const int cv = C / 8, pp = 256 / cv;
+  const int lc = threadIdx.x % cv, prow = threadIdx.x / cv;
+  const int n = blockIdx.y, c = lc * 8;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * slab, p1 = min(hw, p0 + slab);
+  float pv[8], bv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { pv[k] = 1.f; bv[k] = 0.f; }
+  if (pre) load8(pre + static_cast<int64_t>(n) * C + c, pv);
+  if (bias && grad == 0) load8(bias + c, bv);
+  const float ns = noise_strength ? *noise_strength : 1.f;
+  const float* nz_row = noise ? noise + (noise_per_sample ? static_cast<int64_t>(n) * hw : 0) : nullptr;
+  const T* xb = x + static_cast<int64_t>(n) * hw * C + c;
+  const T* yb = yref ? yref + static_cast<int64_t>(n) * hw * C + c : nullptr;
+  T* ob = y + static_cast<int64_t>(n) * hw * C + c;
+  for (int64_t px = p0 + prow; px < p1; px += 2 * pp) {  // two independent pixels per trip: more loads in flight
+    const int64_t px2 = px + pp;
+    const bool two = px2 < p1;
+    float v0[8], v1[8], r0[8], r1[8];
+    load8(xb + px * C, v0);
+    if (two) load8(xb + px2 * C, v1);
+    if (grad == 1 && yb) {
+      load8(yb + px * C, r0);
+      if (two) load8(yb + px2 * C, r1);
+    }
+    float nz0 = 0.f, nz1 = 0.f;
+    if (nz_row && grad == 0) {
+      nz0 = ns * nz_row[px];
+      if (two) nz1 = ns * nz_row[px2];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (grad == 0) {
+        float t0 = fmaf(v0[k], pv[k], nz0 + bv[k]), t1 = fmaf(v1[k], pv[k], nz1 + bv[k]);
+        if (act == 3) { t0 = t0 > 0.f ? t0 : t0 * alpha; t1 = t1 > 0.f ? t1 : t1 * alpha; }
+        t0 *= gain; t1 *= gain;
+        if (clamp >= 0.f) { t0 = fminf(fmaxf(t0, -clamp), clamp); t1 = fminf(fmaxf(t1, -clamp), clamp); }
+        v0[k] = t0; v1[k] = t1;
+      } else {
+        float t0 = v0[k], t1 = v1[k];
+        const float y0 = yb ? r0[k] : 0.f, y1 = yb ? r1[k] : 0.f;
+        if (act == 3) { t0 = y0 > 0.f ? t0 : t0 * alpha; t1 = y1 > 0.f ? t1 : t1 * alpha; }
+        t0 *= gain; t1 *= gain;
+        if (clamp >= 0.f) { t0 = (y0 > -clamp && y0 < clamp) ? t0 : 0.f; t1 = (y1 > -clamp && y1 < clamp) ? t1 : 0.f; }
+        v0[k] = t0 * pv[k]; v1[k] = t1 * pv[k];
+      }
+    }
+    store8(ob + px * C, v0);
+    if (two) store8(ob + px2 * C, v1);
+  }
+}
+
+// out[n,c] += sum_p a*b with every lane busy: 256 threads = 256/cv pixel rows x cv channel vectors (the first version
+// mapped 32 lanes to vectors and left 24 of them idle at C = 64).
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+chan_dot_slab_kernel(const TA* __restrict__ a, const TB* __restrict__ b, float* __restrict__ out, int64_t hw, int C, int slab) {
+  const int cv = C / 8, pp = 256 / cv;
+  const int lc = threadIdx.x % cv, prow = threadIdx.x / cv;
+  const int n = blockIdx.y, c = lc * 8;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * slab, p1 = min(hw, p0 + slab);
+  const TA* ab = a + static_cast<int64_t>(n) * hw * C + c;
+  const TB* bb = b + static_cast<int64_t>(n) * hw * C + c;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t px = p0 + prow; px < p1; px += 2 * pp) {
+    const int64_t px2 = px + pp;
+    float a0[8], b0[8], a1[8], b1[8];
+    load8(ab + px * C, a0);
+    load8(bb + px * C, b0);
+    if (px2 < p1) { load8(ab + px2 * C, a1); load8(bb + px2 * C, b1); }
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a1[k] = 0.f; b1[k] = 0.f; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fmaf(a1[k], b1[k], fmaf(a0[k], b0[k], acc[k]));
+  }
+  __shared__ float red[256];
+  for (int k = 0; k < 8; ++k) {
+    __syncthreads();
+    red[threadIdx.x] = acc[k];
+    __syncthreads();
+    if (prow == 0) {
+      float t = 0.f;
+      for (int r = 0; r < pp; ++r) t += red[r * cv + lc];
+      atomicAdd(out + static_cast<int64_t>(n) * C + c + k, t);
+    }
+  }
+}
+
 // First-order backward of y = clamp(act(x*pre[n,c] + noise[n,p] + bias[c]) * gain) in ONE pass:
 //   t = dy * gain * act'(y) * [|y| < clamp];  dx = t * pre;  dpre[n,c] += sum_p t*x;  dbias_n[n,c] += sum_p t;
 //   dnoise[n,p] = sum_c t
@@ -650,7 +748,12 @@ extern "C" int icgan_chan_dot(const void* a, const void* b, float* out, int N, i
   if (slabs < 1) slabs = 1;
   const int slab = static_cast<int>((hw + slabs - 1) / slabs);
   dim3 grid(static_cast<unsigned>((hw + slab - 1) / slab), static_cast<unsigned>(N));
-#define ICGAN_CD(TA, TB) chan_dot_kernel<TA, TB><<<grid, 256, 0, STREAM>>>(static_cast<const TA*>(a), static_cast<const TB*>(b), out, hw, C, slab)
+  const bool slabbed = C / 8 <= 256 && 256 % (C / 8) == 0;
+#define ICGAN_CD(TA, TB)                                                                                                        \
+  do {                                                                                                                          \
+    if (slabbed) chan_dot_slab_kernel<TA, TB><<<grid, 256, 0, STREAM>>>(static_cast<const TA*>(a), static_cast<const TB*>(b), out, hw, C, slab); \
+    else chan_dot_kernel<TA, TB><<<grid, 256, 0, STREAM>>>(static_cast<const TA*>(a), static_cast<const TB*>(b), out, hw, C, slab);             \
+  } while (0)
   if (a_dtype == ICGAN_BF16 && b_dtype == ICGAN_BF16) ICGAN_CD(__nv_bfloat16, __nv_bfloat16);
   else if (a_dtype == ICGAN_F32 && b_dtype == ICGAN_F32) ICGAN_CD(float, float);
   else if (a_dtype == ICGAN_F32 && b_dtype == ICGAN_BF16) ICGAN_CD(float, __nv_bfloat16);
@@ -696,7 +799,22 @@ extern "C" int icgan_bias_act_nhwc(const void* x, const void* yref, void* y, con
   ICGAN_REQUIRE(grad == 0 || yref || (act == 1 && clamp < 0.f), "icgan_bias_act_nhwc: grad 1 needs the forward output");
   const int64_t total8 = static_cast<int64_t>(N) * hw * C / 8;
   const int g = grid_for(total8);
-#define ICGAN_BA(T) bias_act_vec_kernel<T><<<g, 256, 0, STREAM>>>(static_cast<const T*>(x), static_cast<const T*>(yref), static_cast<T*>(y), bias, pre_scale, noise, noise_strength, noise_per_sample, hw, C, total8, grad, act, alpha, gain, clamp)
+  const int cvv = C / 8;
+  const bool slabbed = cvv <= 256 && 256 % cvv == 0 && hw >= 64;
+  const int pp = slabbed ? 256 / cvv : 1;
+  int slabs = static_cast<int>((static_cast<int64_t>(num_sms()) * 8 + N - 1) / N);
+  const int64_t max_slabs = (hw + 2 * pp - 1) / (2 * pp);
+  if (slabs > max_slabs) slabs = static_cast<int>(max_slabs);
+  if (slabs < 1) slabs = 1;
+  const int slab = static_cast<int>((hw + slabs - 1) / slabs);
+  const dim3 sgrid(static_cast<unsigned>((hw + slab - 1) / slab), static_cast<unsigned>(N));
+#define ICGAN_BA(T)                                                                                                             \
+  do {                                                                                                                          \
+    if (slabbed)                                                                                                                \
+      bias_act_slab_kernel<T><<<sgrid, 256, 0, STREAM>>>(static_cast<const T*>(x), static_cast<const T*>(yref), static_cast<T*>(y), bias, pre_scale, noise, noise_strength, noise_per_sample, hw, C, slab, grad, act, alpha, gain, clamp); \
+    else                                                                                                                        \
+      bias_act_vec_kernel<T><<<g, 256, 0, STREAM>>>(static_cast<const T*>(x), static_cast<const T*>(yref), static_cast<T*>(y), bias, pre_scale, noise, noise_strength, noise_per_sample, hw, C, total8, grad, act, alpha, gain, clamp); \
+  } while (0)
   if (dtype == ICGAN_BF16) ICGAN_BA(__nv_bfloat16);
   else if (dtype == ICGAN_F32) ICGAN_BA(float);
   else { icgan::set_error("icgan_bias_act_nhwc: dtype must be float32 / bfloat16"); return -1; }
