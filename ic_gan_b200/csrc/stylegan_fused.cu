@@ -155,23 +155,31 @@ upfirdn2d_direct_kernel(const T* __restrict__ x, T* __restrict__ y, const Upfird
   const int ux = ox * DOWN - p.pad0x;
   int u_cur = oy0 * DOWN - p.pad0y;
   const T* xn = x + static_cast<int64_t>(n) * p.inH * p.inW * p.C + c0;
+  // column offsets and validity of the four horizontal taps never change while the thread walks down its strip
+  int col_off[F];
+  bool col_ok[F];
+#pragma unroll
+  for (int t = 0; t < F; ++t) {
+    const int u = ux + t;
+    int ix = u;
+    bool ok = live;
+    if (UP == 2) { ok = ok && ((u & 1) == 0); ix = u >> 1; }
+    col_ok[t] = ok && ix >= 0 && ix < p.inW;
+    col_off[t] = ix * p.C;
+  }
+  const int row_pitch = p.inW * p.C;
   auto load_hrow = [&](int u_row, float (&dst)[NV]) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) dst[k] = 0.f;
-    bool row_ok = live;
     int iy = u_row;
-    if (UP == 2) { row_ok = row_ok && ((u_row & 1) == 0); iy = u_row >> 1; }
+    bool row_ok = true;
+    if (UP == 2) { row_ok = (u_row & 1) == 0; iy = u_row >> 1; }
     row_ok = row_ok && iy >= 0 && iy < p.inH;
+    const T* rowp = xn + static_cast<int64_t>(iy) * row_pitch;
     uint4 raw[F];
 #pragma unroll
-    for (int t = 0; t < F; ++t) {
-      const int u = ux + t;
-      bool ok = row_ok;
-      int ix = u;
-      if (UP == 2) { ok = ok && ((u & 1) == 0); ix = u >> 1; }
-      ok = ok && ix >= 0 && ix < p.inW;
-      raw[t] = ok ? __ldg(reinterpret_cast<const uint4*>(xn + (static_cast<int64_t>(iy) * p.inW + ix) * p.C)) : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int t = 0; t < F; ++t)
+      raw[t] = (row_ok && col_ok[t]) ? __ldg(reinterpret_cast<const uint4*>(rowp + col_off[t])) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int t = 0; t < F; ++t) {
       float xv[NV];
@@ -185,7 +193,7 @@ upfirdn2d_direct_kernel(const T* __restrict__ x, T* __restrict__ y, const Upfird
 #pragma unroll
   for (int r = 0; r < F; ++r) load_hrow(u_cur + r, hwin[r]);
   const float ns = p.post.noise_strength ? *p.post.noise_strength : 1.f;
-#pragma unroll 2
+#pragma unroll 4  // a multiple of the window depth: the row rotation below becomes register renaming, not moves
   for (int ro = 0; ro < ROWS; ++ro) {
     const int oy = oy0 + ro;
     if (oy >= p.outH) break;
