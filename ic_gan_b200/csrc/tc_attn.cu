@@ -1,0 +1,576 @@
+// Fused non-local block core (layers.Attention.forward, BigGAN_PyTorch/layers.py:233-243) on tcgen05:
+//     beta = softmax_k(theta phi^T),  o = beta g          theta [B,Q,d], pooled phi [B,Kk,d], pooled g [B,Kk,dv]  (bf16)
+// without the [B,Q,Kk] float32 logits ever leaving the SM.
+//
+//   attn_fwd_kernel    one CTA per 128 query rows.  The logits of a 128-key chunk are one UMMA (accumulator in TMEM); the
+//                      four softmax warps own one query row per thread (TMEM lane = row), so row maxima and sums need no
+//                      shuffles.  Pass 1 walks the Kk/128 chunks for the row's log-sum-exp; pass 2 recomputes each chunk,
+//                      writes exp2(s*log2e - lse) as bf16 straight into a SWIZZLE_128B K-major tile in shared memory and
+//                      the MMA warp accumulates  O += P g  from it (g is read as an MN-major operand from the very tile
+//                      TMA wrote).  The probabilities are also stored to global memory when the backward will want them
+//                      (dg = P^T dO stays a batched GEMM).
+//   attn_bwd_q_kernel  same tiling for the query-side backward:  P recomputed from the saved log-sum-exp,
+//                      dP = dO g^T (second TMEM accumulator), dS = P (dP - rowsum(dO o)) written as bf16 to shared memory
+//                      (operand of  dtheta += dS phi, third accumulator; phi is the tile already loaded for the logits, read
+//                      MN-major) and to global memory (operand of the batched GEMM dphi = dS^T theta).
+//
+// Warp roles in both kernels: warp 0 = TMA producer, warp 1 = MMA issuer (and TMEM owner), warps 2-5 = softmax / epilogue
+// (warp w works on TMEM lanes 32 (w mod 4) ..).  Persistent over (sample, query tile); every ring is driven by running
+// counters so phases carry across tiles.
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace icgan {
+namespace {
+
+constexpr int kAttnThreads = 192;
+constexpr uint32_t kTile = 16384u;  // 128 rows x 128 bytes (64 bf16), one SWIZZLE_128B operand tile
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnParams {
+  int B, Q, Kk, d, dv;
+  int q_tiles, total_tiles, n_chunks, d_steps, v_boxes, dv_steps;
+  uint32_t idesc_s, idesc_o, idesc_dq;
+  const __nv_bfloat16* O_in;   // backward: forward output
+  const __nv_bfloat16* dO;     // backward: incoming gradient
+  __nv_bfloat16* O;            // forward output [B,Q,dv]
+  __nv_bfloat16* P;            // forward: probabilities [B,Q,Kk] or nullptr;  backward: dS [B,Q,Kk]
+  __nv_bfloat16* dTheta;       // backward [B,Q,d]
+  float* lse2;                 // [B,Q] log2-domain log-sum-exp: written by the forward (nullable), read by the backward
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Thread `row` of a 128-row K-major SWIZZLE_128B operand writes 32 consecutive K elements (columns col0 .. col0+31 of a
+// 128-column chunk held as two 64-column tiles).  Element k of row r lives at  tile + r*128 + ((k/8 ^ (r & 7)) << 4).
+__device__ __forceinline__ void store_row_block(uint32_t chunk_addr, int row, int blk, const uint32_t (&w)[16]) {
+  const uint32_t tile = chunk_addr + static_cast<uint32_t>(blk >> 1) * kTile + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const uint32_t cidx = static_cast<uint32_t>((blk & 1) * 4 + ch);
+    st_shared_v4(tile + ((cidx ^ static_cast<uint32_t>(row & 7)) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2],
+                 w[4 * ch + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------- forward
+// shared memory: theta[2] | phi[2] | g[2] (3 tiles each) | P[2] (2 tiles each) | barriers
+constexpr uint32_t kFwdTheta = 0, kFwdPhi = 2 * kTile, kFwdG = 4 * kTile, kFwdP = 10 * kTile, kFwdBars = 14 * kTile;
+constexpr uint32_t kFwdSmem = kFwdBars + 256u + 1024u;
+enum FwdBar { F_TH_FULL = 0, F_TH_EMPTY = 2, F_PH_FULL = 4, F_PH_EMPTY = 6, F_G_FULL = 8, F_G_EMPTY = 10, F_S_FULL = 12,
+              F_S_EMPTY = 14, F_P_FULL = 16, F_P_EMPTY = 18, F_O_FULL = 20, F_O_EMPTY = 21, F_NBARS = 22 };
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_constant__ CUtensorMap tmPhi,
+                const __grid_constant__ CUtensorMap tmG, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFwdBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + F_NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < F_NBARS; ++i) {
+      const bool four = (i == F_S_EMPTY || i == F_S_EMPTY + 1 || i == F_P_FULL || i == F_P_FULL + 1 || i == F_O_EMPTY);
+      mbar_init(&bars[i], four ? 4u : 1u);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nc = p.n_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmTheta);
+      tma_prefetch_desc(&tmPhi);
+      tma_prefetch_desc(&tmG);
+    }
+    uint32_t tl = 0, fi = 0, gi = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const int b = tile / p.q_tiles, q0 = (tile % p.q_tiles) * 128;
+      const uint32_t tb = tl & 1u;
+      mbar_wait(&bars[F_TH_EMPTY + tb], ((tl >> 1) & 1u) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&bars[F_TH_FULL + tb], kTile);
+        tma_load_3d(smem + kFwdTheta + tb * kTile, &tmTheta, &bars[F_TH_FULL + tb], 0, q0, b);
+      }
+      __syncwarp();
+      for (int item = 0; item < 2 * nc; ++item) {
+        const int c = item < nc ? item : item - nc;
+        const uint32_t slot = fi & 1u;
+        mbar_wait(&bars[F_PH_EMPTY + slot], ((fi >> 1) & 1u) ^ 1u);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars[F_PH_FULL + slot], kTile);
+          tma_load_3d(smem + kFwdPhi + slot * kTile, &tmPhi, &bars[F_PH_FULL + slot], 0, c * 128, b);
+        }
+        __syncwarp();
+        ++fi;
+        if (item >= nc) {
+          const uint32_t gs = gi & 1u;
+          mbar_wait(&bars[F_G_EMPTY + gs], ((gi >> 1) & 1u) ^ 1u);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&bars[F_G_FULL + gs], static_cast<uint32_t>(p.v_boxes) * kTile);
+            for (int j = 0; j < p.v_boxes; ++j)
+              tma_load_3d(smem + kFwdG + (gs * 3u + j) * kTile, &tmG, &bars[F_G_FULL + gs], j * 64, c * 128, b);
+          }
+          __syncwarp();
+          ++gi;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t tl = 0, fi = 0, gi = 0, si = 0, pi = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t tb = tl & 1u;
+      mbar_wait(&bars[F_TH_FULL + tb], (tl >> 1) & 1u);
+      const uint64_t da = umma_desc_kmajor(base + kFwdTheta + tb * kTile, 128);
+      // O += P_j g_j for chunk j of this tile
+      auto issue_pv = [&](int j, bool last) {
+        const uint32_t gs = gi & 1u, pb = pi & 1u;
+        mbar_wait(&bars[F_G_FULL + gs], (gi >> 1) & 1u);
+        mbar_wait(&bars[F_P_FULL + pb], (pi >> 1) & 1u);
+        if (j == 0) mbar_wait(&bars[F_O_EMPTY], (tl & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t db = desc_mn(base + kFwdG + gs * 3u * kTile, kTile);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t dp = umma_desc_kmajor(base + kFwdP + (pb * 2u + (ks >> 2)) * kTile, 128) + 2u * (ks & 3);
+            umma_bf16(tmem_base + 256u, dp, db + 128u * ks, p.idesc_o, (j | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars[F_G_EMPTY + gs]);
+          umma_commit(&bars[F_P_EMPTY + pb]);
+          if (last) umma_commit(&bars[F_O_FULL]);
+        }
+        __syncwarp();
+        ++gi;
+        ++pi;
+      };
+      for (int item = 0; item < 2 * nc; ++item) {
+        const uint32_t slot = fi & 1u, sb = si & 1u;
+        mbar_wait(&bars[F_PH_FULL + slot], (fi >> 1) & 1u);
+        mbar_wait(&bars[F_S_EMPTY + sb], ((si >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t db = umma_desc_kmajor(base + kFwdPhi + slot * kTile, 128);
+          for (int k = 0; k < p.d_steps; ++k)
+            umma_bf16(tmem_base + sb * 128u, da + 2u * k, db + 2u * k, p.idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&bars[F_PH_EMPTY + slot]);
+          umma_commit(&bars[F_S_FULL + sb]);
+          if (item == 2 * nc - 1) umma_commit(&bars[F_TH_EMPTY + tb]);
+        }
+        __syncwarp();
+        ++fi;
+        ++si;
+        if (item > nc) issue_pv(item - 1 - nc, false);
+      }
+      issue_pv(nc - 1, true);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t tl = 0, si = 0, pi = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const int b = tile / p.q_tiles, q0 = (tile % p.q_tiles) * 128;
+      const int64_t grow = static_cast<int64_t>(b) * p.Q + q0 + row;
+      float m = -INFINITY, l = 0.f;
+      for (int c = 0; c < nc; ++c) {  // pass 1: running maximum and sum of the row, log2 domain
+        const uint32_t sb = si & 1u;
+        mbar_wait(&bars[F_S_FULL + sb], (si >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {
+          uint32_t r[32];
+          tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(blk * 32), r);
+          tmem_ld_wait();
+          float bm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bm = fmaxf(bm, __uint_as_float(r[j]));
+          const float mn = fmaxf(m, bm * kLog2e);
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += ex2(fmaf(__uint_as_float(r[j]), kLog2e, -mn));
+          l = fmaf(l, ex2(m - mn), acc);
+          m = mn;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[F_S_EMPTY + sb]);
+        ++si;
+      }
+      const float lse = m + log2f(l);
+      if (p.lse2) p.lse2[grow] = lse;
+      __nv_bfloat16* prow = p.P ? p.P + grow * p.Kk : nullptr;
+      for (int c = 0; c < nc; ++c) {  // pass 2: normalised probabilities -> shared memory (-> global)
+        const uint32_t sb = si & 1u, pb = pi & 1u;
+        mbar_wait(&bars[F_S_FULL + sb], (si >> 1) & 1u);
+        mbar_wait(&bars[F_P_EMPTY + pb], ((pi >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {
+          uint32_t r[32];
+          tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(blk * 32), r);
+          tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            w[j] = pack_bf16(ex2(fmaf(__uint_as_float(r[2 * j]), kLog2e, -lse)),
+                             ex2(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -lse)));
+          store_row_block(base + kFwdP + pb * 2u * kTile, row, blk, w);
+          if (prow) {
+            uint4* dst = reinterpret_cast<uint4*>(prow + c * 128 + blk * 32);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars[F_P_FULL + pb]);
+          mbar_arrive(&bars[F_S_EMPTY + sb]);
+        }
+        ++si;
+        ++pi;
+      }
+      mbar_wait(&bars[F_O_FULL], tl & 1u);
+      tc_fence_after();
+      __nv_bfloat16* orow = p.O + grow * p.dv;
+      for (int c0 = 0; c0 < p.dv; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + 256u + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[F_O_EMPTY]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------- backward, query side
+// shared memory: theta | dO (3 tiles) | phi[2] | g (3 tiles) | dS (2 tiles) | barriers
+constexpr uint32_t kBwdTheta = 0, kBwdDO = kTile, kBwdPhi = 4 * kTile, kBwdG = 6 * kTile, kBwdDS = 9 * kTile,
+                   kBwdBars = 11 * kTile;
+constexpr uint32_t kBwdSmem = kBwdBars + 256u + 1024u;
+enum BwdBar { Q_TD_FULL = 0, Q_TD_EMPTY = 1, Q_PH_FULL = 2, Q_PH_EMPTY = 4, Q_G_FULL = 6, Q_G_EMPTY = 7, Q_S_FULL = 8,
+              Q_S_EMPTY = 10, Q_DP_FULL = 12, Q_DP_EMPTY = 13, Q_DS_FULL = 14, Q_DS_EMPTY = 15, Q_DT_FULL = 16,
+              Q_DT_EMPTY = 17, Q_NBARS = 18 };
+// TMEM columns: logits [0,128) and [128,256), dP [256,384), dtheta [384,448)
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_constant__ CUtensorMap tmPhi,
+                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmDO,
+                  const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Q_NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Q_NBARS; ++i) {
+      const bool four = (i == Q_S_EMPTY || i == Q_S_EMPTY + 1 || i == Q_DP_EMPTY || i == Q_DS_FULL || i == Q_DT_EMPTY);
+      mbar_init(&bars[i], four ? 4u : 1u);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nc = p.n_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmTheta);
+      tma_prefetch_desc(&tmPhi);
+      tma_prefetch_desc(&tmG);
+      tma_prefetch_desc(&tmDO);
+    }
+    uint32_t tl = 0, fi = 0, gi = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const int b = tile / p.q_tiles, q0 = (tile % p.q_tiles) * 128;
+      mbar_wait(&bars[Q_TD_EMPTY], (tl & 1u) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&bars[Q_TD_FULL], static_cast<uint32_t>(1 + p.v_boxes) * kTile);
+        tma_load_3d(smem + kBwdTheta, &tmTheta, &bars[Q_TD_FULL], 0, q0, b);
+        for (int j = 0; j < p.v_boxes; ++j)
+          tma_load_3d(smem + kBwdDO + j * kTile, &tmDO, &bars[Q_TD_FULL], j * 64, q0, b);
+      }
+      __syncwarp();
+      for (int c = 0; c < nc; ++c) {
+        const uint32_t slot = fi & 1u;
+        mbar_wait(&bars[Q_PH_EMPTY + slot], ((fi >> 1) & 1u) ^ 1u);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars[Q_PH_FULL + slot], kTile);
+          tma_load_3d(smem + kBwdPhi + slot * kTile, &tmPhi, &bars[Q_PH_FULL + slot], 0, c * 128, b);
+        }
+        __syncwarp();
+        ++fi;
+        mbar_wait(&bars[Q_G_EMPTY], (gi & 1u) ^ 1u);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars[Q_G_FULL], static_cast<uint32_t>(p.v_boxes) * kTile);
+          for (int j = 0; j < p.v_boxes; ++j)
+            tma_load_3d(smem + kBwdG + j * kTile, &tmG, &bars[Q_G_FULL], j * 64, c * 128, b);
+        }
+        __syncwarp();
+        ++gi;
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t tl = 0, fi = 0, gi = 0, si = 0, di = 0, fq = 0;  // fq: phi ring position of the next dtheta product
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      mbar_wait(&bars[Q_TD_FULL], tl & 1u);
+      const uint64_t da_theta = umma_desc_kmajor(base + kBwdTheta, 128);
+      // dtheta += dS_j phi_j
+      auto issue_dq = [&](int j, bool last) {
+        const uint32_t slot = fq & 1u;
+        mbar_wait(&bars[Q_DS_FULL], di & 1u);
+        if (j == 0) mbar_wait(&bars[Q_DT_EMPTY], (tl & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t db = desc_mn(base + kBwdPhi + slot * kTile, kTile);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t dsd = umma_desc_kmajor(base + kBwdDS + static_cast<uint32_t>(ks >> 2) * kTile, 128) +
+                                 2u * (ks & 3);
+            umma_bf16(tmem_base + 384u, dsd, db + 128u * ks, p.idesc_dq, (j | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars[Q_DS_EMPTY]);
+          umma_commit(&bars[Q_PH_EMPTY + slot]);
+          if (last) umma_commit(&bars[Q_DT_FULL]);
+        }
+        __syncwarp();
+        ++di;
+        ++fq;
+      };
+      for (int c = 0; c < nc; ++c) {
+        const uint32_t slot = fi & 1u, sb = si & 1u;
+        mbar_wait(&bars[Q_PH_FULL + slot], (fi >> 1) & 1u);
+        mbar_wait(&bars[Q_S_EMPTY + sb], ((si >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t db = umma_desc_kmajor(base + kBwdPhi + slot * kTile, 128);
+          for (int k = 0; k < p.d_steps; ++k)
+            umma_bf16(tmem_base + sb * 128u, da_theta + 2u * k, db + 2u * k, p.idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&bars[Q_S_FULL + sb]);
+        }
+        __syncwarp();
+        ++fi;
+        ++si;
+        mbar_wait(&bars[Q_G_FULL], gi & 1u);
+        mbar_wait(&bars[Q_DP_EMPTY], (gi & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          for (int ks = 0; ks < p.dv_steps; ++ks) {
+            const uint32_t off = static_cast<uint32_t>(ks >> 2) * kTile;
+            const uint64_t da = umma_desc_kmajor(base + kBwdDO + off, 128) + 2u * (ks & 3);
+            const uint64_t db = umma_desc_kmajor(base + kBwdG + off, 128) + 2u * (ks & 3);
+            umma_bf16(tmem_base + 256u, da, db, p.idesc_s, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars[Q_G_EMPTY]);
+          umma_commit(&bars[Q_DP_FULL]);
+          if (c == nc - 1) umma_commit(&bars[Q_TD_EMPTY]);  // theta and dO have no reader after this product
+        }
+        __syncwarp();
+        ++gi;
+        if (c > 0) issue_dq(c - 1, false);
+      }
+      issue_dq(nc - 1, true);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t tl = 0, si = 0, gi = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const int b = tile / p.q_tiles, q0 = (tile % p.q_tiles) * 128;
+      const int64_t grow = static_cast<int64_t>(b) * p.Q + q0 + row;
+      const float lse = p.lse2[grow];
+      float dsum = 0.f;  // rowsum(dO * o) = rowsum(dP * P)
+      {
+        const uint4* a = reinterpret_cast<const uint4*>(p.dO + grow * p.dv);
+        const uint4* o = reinterpret_cast<const uint4*>(p.O_in + grow * p.dv);
+        for (int j = 0; j < p.dv / 8; ++j) {
+          const uint4 x = a[j], y = o[j];
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[e]));
+            const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[e]));
+            dsum = fmaf(fx.x, fy.x, dsum);
+            dsum = fmaf(fx.y, fy.y, dsum);
+          }
+        }
+      }
+      __nv_bfloat16* dsrow = p.P + grow * p.Kk;
+      for (int c = 0; c < nc; ++c) {
+        const uint32_t sb = si & 1u;
+        mbar_wait(&bars[Q_S_FULL + sb], (si >> 1) & 1u);
+        mbar_wait(&bars[Q_DP_FULL], gi & 1u);
+        mbar_wait(&bars[Q_DS_EMPTY], (gi & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {
+          uint32_t r[32], g[32];
+          tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(blk * 32), r);
+          tmem_ld32(taddr + 256u + static_cast<uint32_t>(blk * 32), g);
+          tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2(fmaf(__uint_as_float(r[2 * j]), kLog2e, -lse));
+            const float p1 = ex2(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -lse));
+            w[j] = pack_bf16(p0 * (__uint_as_float(g[2 * j]) - dsum), p1 * (__uint_as_float(g[2 * j + 1]) - dsum));
+          }
+          store_row_block(base + kBwdDS, row, blk, w);
+          uint4* dst = reinterpret_cast<uint4*>(dsrow + c * 128 + blk * 32);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars[Q_S_EMPTY + sb]);
+          mbar_arrive(&bars[Q_DP_EMPTY]);
+          mbar_arrive(&bars[Q_DS_FULL]);
+        }
+        ++si;
+        ++gi;
+      }
+      mbar_wait(&bars[Q_DT_FULL], tl & 1u);
+      tc_fence_after();
+      __nv_bfloat16* trow = p.dTheta + grow * p.d;
+      for (int c0 = 0; c0 < p.d; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + 384u + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        uint4* dst = reinterpret_cast<uint4*>(trow + c0);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (c0 + 8 < p.d) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[Q_DT_EMPTY]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int fill_params(AttnParams* p, int B, int Q, int Kk, int d, int dv, const char* who) {
+  ICGAN_REQUIRE(B > 0 && Q > 0 && Kk > 0 && Q % 128 == 0 && Kk % 128 == 0,
+                "%s: Q (%d) and Kk (%d) must be multiples of 128", who, Q, Kk);
+  ICGAN_REQUIRE(d >= 8 && d <= 64 && d % 8 == 0, "%s: d = %d must be a multiple of 8 in [8, 64]", who, d);
+  ICGAN_REQUIRE(dv >= 16 && dv <= 192 && dv % 16 == 0, "%s: dv = %d must be a multiple of 16 in [16, 192]", who, dv);
+  p->B = B; p->Q = Q; p->Kk = Kk; p->d = d; p->dv = dv;
+  p->q_tiles = Q / 128;
+  p->total_tiles = B * p->q_tiles;
+  p->n_chunks = Kk / 128;
+  p->d_steps = (d + 15) / 16;
+  p->dv_steps = dv / 16;
+  p->v_boxes = (dv + 63) / 64;
+  p->idesc_s = umma_idesc_bf16(128, 128);
+  p->idesc_o = umma_idesc_bf16(128, static_cast<uint32_t>(dv)) | (1u << 16);
+  p->idesc_dq = umma_idesc_bf16(128, static_cast<uint32_t>(p->d_steps * 16)) | (1u << 16);
+  return 0;
+}
+
+}  // namespace
+}  // namespace icgan
+
+using namespace icgan;
+
+extern "C" int icgan_attn_fwd(const void* theta, const void* phi, const void* g, void* o, void* probs, float* lse2,
+                              int B, int Q, int Kk, int d, int dv, void* stream) {
+  ICGAN_REQUIRE(theta && phi && g && o, "icgan_attn_fwd: null pointer");
+  AttnParams p{};
+  if (int rc = fill_params(&p, B, Q, Kk, d, dv, "icgan_attn_fwd")) return rc;
+  p.O = static_cast<__nv_bfloat16*>(o);
+  p.P = static_cast<__nv_bfloat16*>(probs);
+  p.lse2 = lse2;
+  CUtensorMap tmT, tmP, tmG;
+  if (int rc = make_map3(&tmT, theta, d, Q, B, d, static_cast<uint64_t>(Q) * d, 64, 128)) return rc;
+  if (int rc = make_map3(&tmP, phi, d, Kk, B, d, static_cast<uint64_t>(Kk) * d, 64, 128)) return rc;
+  if (int rc = make_map3(&tmG, g, dv, Kk, B, dv, static_cast<uint64_t>(Kk) * dv, 64, 128)) return rc;
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured))
+    ICGAN_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_attn_bwd_q(const void* theta, const void* phi, const void* g, const void* o, const void* dout,
+                                const float* lse2, void* dtheta, void* ds, int B, int Q, int Kk, int d, int dv,
+                                void* stream) {
+  ICGAN_REQUIRE(theta && phi && g && o && dout && lse2 && dtheta && ds, "icgan_attn_bwd_q: null pointer");
+  AttnParams p{};
+  if (int rc = fill_params(&p, B, Q, Kk, d, dv, "icgan_attn_bwd_q")) return rc;
+  p.O_in = static_cast<const __nv_bfloat16*>(o);
+  p.dO = static_cast<const __nv_bfloat16*>(dout);
+  p.P = static_cast<__nv_bfloat16*>(ds);
+  p.dTheta = static_cast<__nv_bfloat16*>(dtheta);
+  p.lse2 = const_cast<float*>(lse2);
+  CUtensorMap tmT, tmP, tmG, tmD;
+  if (int rc = make_map3(&tmT, theta, d, Q, B, d, static_cast<uint64_t>(Q) * d, 64, 128)) return rc;
+  if (int rc = make_map3(&tmP, phi, d, Kk, B, d, static_cast<uint64_t>(Kk) * d, 64, 128)) return rc;
+  if (int rc = make_map3(&tmG, g, dv, Kk, B, dv, static_cast<uint64_t>(Kk) * dv, 64, 128)) return rc;
+  if (int rc = make_map3(&tmD, dout, dv, Q, B, dv, static_cast<uint64_t>(Q) * dv, 64, 128)) return rc;
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured))
+    ICGAN_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  attn_bwd_q_kernel<<<grid, kAttnThreads, kBwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, tmD, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}

@@ -863,6 +863,10 @@ def _gemm_tc(A, B_, Cm, M, N, K, batch, a_mn, b_mn, lda, sab, ldb, sbb, ldc, scb
                         sbb, ldc, scb, float(alpha), dt(Cm), stream_ptr()))
 
 
+# 1: the non-local block's logits stay in tensor memory (csrc/tc_attn.cu); 0: three batched GEMMs around fp32 logits in HBM.
+FUSED_ATTENTION = __import__("os").environ.get("ICGAN_FUSED_ATTENTION", "1") != "0"
+
+
 class AttentionCoreFn(torch.autograd.Function):
     """o[b,q,:] = sum_k softmax_k(theta[b,q,:] . phi[b,k,:]) * g[b,k,:]   (layers.py:233-243) on NHWC-flattened
     theta [B,Q,d], pooled phi [B,Kk,d], pooled g [B,Kk,dv].  bfloat16 inputs run on the batched tcgen05 GEMM (logits and
@@ -874,6 +878,19 @@ class AttentionCoreFn(torch.autograd.Function):
         B, Q, d = theta.shape
         Kk, dv = phi.shape[1], g.shape[2]
         tc = theta.dtype == torch.bfloat16 and d % 8 == 0 and dv % 8 == 0 and Kk % 8 == 0
+        ctx.fused = (tc and FUSED_ATTENTION and Q % 128 == 0 and Kk % 128 == 0 and d <= 64 and dv % 16 == 0
+                     and dv <= 192)
+        if ctx.fused:  # logits live in tensor memory only (csrc/tc_attn.cu)
+            o = torch.empty(B, Q, dv, device=theta.device, dtype=theta.dtype)
+            grad = any(ctx.needs_input_grad)
+            P = torch.empty(B, Q, Kk, device=theta.device, dtype=theta.dtype) if grad else None
+            lse = torch.empty(B, Q, device=theta.device, dtype=torch.float32) if grad else None
+            call("icgan_attn_fwd", ptr(theta), ptr(phi), ptr(g), ptr(o), ptr(P), ptr(lse), B, Q, Kk, d, dv,
+                 stream_ptr())
+            ctx.tc = True
+            if grad:
+                ctx.save_for_backward(theta, phi, g, P, o, lse)
+            return o
         S = torch.empty(B, Q, Kk, device=theta.device, dtype=torch.float32)
         if tc:
             _gemm_tc(theta, phi, S, Q, Kk, d, B, 0, 0, d, Q * d, d, Kk * d, Kk, Q * Kk)
@@ -893,8 +910,19 @@ class AttentionCoreFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, do):
-        theta, phi, g, P = ctx.saved_tensors
         do = do.contiguous()
+        if ctx.fused:
+            theta, phi, g, P, o, lse = ctx.saved_tensors
+            B, Q, d = theta.shape
+            Kk, dv = phi.shape[1], g.shape[2]
+            dtheta, dphi, dg = torch.empty_like(theta), torch.empty_like(phi), torch.empty_like(g)
+            dS = torch.empty_like(P)
+            call("icgan_attn_bwd_q", ptr(theta), ptr(phi), ptr(g), ptr(o), ptr(do), ptr(lse), ptr(dtheta), ptr(dS),
+                 B, Q, Kk, d, dv, stream_ptr())
+            _gemm_tc(P, do, dg, Kk, dv, Q, B, 1, 1, Kk, Q * Kk, dv, Q * dv, dv, Kk * dv)
+            _gemm_tc(dS, theta, dphi, Kk, d, Q, B, 1, 1, Kk, Q * Kk, d, Q * d, d, Kk * d)
+            return dtheta, dphi, dg
+        theta, phi, g, P = ctx.saved_tensors
         B, Q, d = theta.shape
         Kk, dv = phi.shape[1], g.shape[2]
         tc = ctx.tc
