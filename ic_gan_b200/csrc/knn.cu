@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace icgan {
 namespace {
@@ -29,20 +30,6 @@ constexpr int kKnnKC = 64;    // reduction elements per pipeline stage
 constexpr int kKnnMaxC = 64;  // candidates kept per query row
 constexpr uint32_t kKnnSmem = 227u * 1024u;
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
 int make_map2(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   ICGAN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace icgan {
 
@@ -30,22 +31,6 @@ static constexpr int kConvThreads = 320;  // 2 role warps + 8 epilogue warps
 static constexpr uint32_t kSmemBudget = 227u * 1024u;
 
 // ------------------------------------------------------------------------------------------------ tensor maps
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // bf16 tensor, dims[0] fastest. strides_bytes[i] is the stride of dims[i+1].
 // elem_strides (optional): TMA traversal stride per dimension -- with stride s a box spanning box[i] tensor elements
 // delivers ceil(box[i] / s) of them (every s-th), which is how the stride-2 convolutions read their input.

@@ -11,7 +11,19 @@ namespace icgan {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled is a driver-API call and wants a context current on the calling thread.  A thread that has so
+// far only hit PyTorch's caching allocator (an autograd worker whose first kernel is one of ours) has none: one runtime
+// call binds the device's primary context to it.
+inline void bind_primary_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 inline EncodeTiledFn encode_fn() {
+  bind_primary_context();
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
