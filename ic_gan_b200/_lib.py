@@ -79,8 +79,9 @@ SIGNATURES = {
     "icgan_adam_ema_step": [fp, fp, fp, fp, fp, i64, f64, f64, f64, f64, i64, f64, f64, vp],
     "icgan_ema_lerp": [fp, fp, i64, f64, vp],
     "icgan_gemm_tc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
-    "icgan_attn_fwd": [vp, vp, vp, vp, vp, fp, i32, i32, i32, i32, i32, vp],
-    "icgan_attn_bwd_q": [vp, vp, vp, vp, vp, fp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "icgan_attn_fwd": [vp, vp, vp, vp, fp, i32, i32, i32, i32, i32, vp],
+    "icgan_attn_bwd_q": [vp, vp, vp, vp, vp, fp, vp, vp, fp, i32, i32, i32, i32, i32, vp],
+    "icgan_attn_bwd_kv": [vp, vp, vp, vp, fp, fp, vp, vp, i32, i32, i32, i32, i32, vp],
     "icgan_gemm": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, fp, f32, fp, i32,
                    i32, i32, vp],
 }

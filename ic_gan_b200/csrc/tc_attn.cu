@@ -2,21 +2,26 @@
 //     beta = softmax_k(theta phi^T),  o = beta g          theta [B,Q,d], pooled phi [B,Kk,d], pooled g [B,Kk,dv]  (bf16)
 // without the [B,Q,Kk] float32 logits ever leaving the SM.
 //
-//   attn_fwd_kernel    one CTA per 128 query rows.  The logits of a 128-key chunk are one UMMA (accumulator in TMEM); the
-//                      four softmax warps own one query row per thread (TMEM lane = row), so row maxima and sums need no
-//                      shuffles.  Pass 1 walks the Kk/128 chunks for the row's log-sum-exp; pass 2 recomputes each chunk,
-//                      writes exp2(s*log2e - lse) as bf16 straight into a SWIZZLE_128B K-major tile in shared memory and
-//                      the MMA warp accumulates  O += P g  from it (g is read as an MN-major operand from the very tile
-//                      TMA wrote).  The probabilities are also stored to global memory when the backward will want them
-//                      (dg = P^T dO stays a batched GEMM).
+//   attn_fwd_kernel    one CTA per 128 query rows.  The logits of a 128-key chunk are one UMMA (accumulator in TMEM); a
+//                      softmax thread owns one query row (TMEM lane = row) and 64 of the chunk's columns, so row maxima
+//                      and sums need no shuffles, only one exchange between the two column halves.  Pass 1 walks the
+//                      Kk/128 chunks for the row maximum; pass 2 recomputes each chunk, writes exp2(s log2e - max) as
+//                      bf16 straight into a SWIZZLE_128B K-major tile in shared memory and the MMA warp accumulates
+//                      O += P g  from it (g is read as an MN-major operand from the very tile TMA wrote); the row sum
+//                      divides O on the way out and gives the log-sum-exp the backward restarts from.
 //   attn_bwd_q_kernel  same tiling for the query-side backward:  P recomputed from the saved log-sum-exp,
 //                      dP = dO g^T (second TMEM accumulator), dS = P (dP - rowsum(dO o)) written as bf16 to shared memory
 //                      (operand of  dtheta += dS phi, third accumulator; phi is the tile already loaded for the logits, read
-//                      MN-major) and to global memory (operand of the batched GEMM dphi = dS^T theta).
+//                      MN-major).  rowsum(dO o) is also written out for the key side.
+//   attn_bwd_kv_kernel one CTA per 128 keys, walking the queries 64 at a time:  S^T = phi theta^T and dP^T = g dO^T
+//                      (double-buffered TMEM accumulators, thread = key row, the per-query log-sum-exp and rowsum arrive
+//                      with the stage as two 256-byte bulk copies), P^T and dS^T as bf16 K-major tiles in shared memory,
+//                      dg += P^T dO and dphi += dS^T theta accumulate in TMEM over the whole walk (dO and theta are the
+//                      stage's own tiles read MN-major).  Neither P nor dS ever exists in HBM.
 //
-// Warp roles in both kernels: warp 0 = TMA producer, warp 1 = MMA issuer (and TMEM owner), warps 2-5 = softmax / epilogue
-// (warp w works on TMEM lanes 32 (w mod 4) ..).  Persistent over (sample, query tile); every ring is driven by running
-// counters so phases carry across tiles.
+// Warp roles in all three: warp 0 = TMA producer, warp 1 = MMA issuer (and TMEM owner), the rest = softmax / epilogue
+// (warp w works on TMEM lanes 32 (w mod 4) ..).  Persistent over (sample, tile); every ring is driven by running counters
+// so phases carry across tiles.
 #include <cuda.h>
 #include <math.h>
 
@@ -41,6 +46,10 @@ struct AttnParams {
   __nv_bfloat16* P;            // forward: probabilities [B,Q,Kk] or nullptr;  backward: dS [B,Q,Kk]
   __nv_bfloat16* dTheta;       // backward [B,Q,d]
   float* lse2;                 // [B,Q] log2-domain log-sum-exp: written by the forward (nullable), read by the backward
+  float* dsum;                 // [B,Q] rowsum(dO * o): written by the query-side backward (nullable), read by the key side
+  __nv_bfloat16* dPhi;         // key-side backward [B,Kk,d]
+  __nv_bfloat16* dG;           // key-side backward [B,Kk,dv]
+  uint32_t idesc_s64;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -73,11 +82,14 @@ __device__ __forceinline__ void store_row_block(uint32_t chunk_addr, int row, in
 // ------------------------------------------------------------------------------------------------------------- forward
 // shared memory: theta[2] | phi[2] | g[2] (3 tiles each) | P[2] (2 tiles each) | barriers
 constexpr uint32_t kFwdTheta = 0, kFwdPhi = 2 * kTile, kFwdG = 4 * kTile, kFwdP = 10 * kTile, kFwdBars = 14 * kTile;
-constexpr uint32_t kFwdSmem = kFwdBars + 256u + 1024u;
+constexpr uint32_t kFwdXch = kFwdBars + 256u;  // 1.5 KB: row maxima / sums exchanged between the two column halves
+constexpr uint32_t kFwdSmem = kFwdXch + 1536u + 1024u;
+constexpr int kFwdThreads = 320;  // TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quadrant)
+static_assert(kFwdSmem <= 227u * 1024u, "forward tile set exceeds shared memory");
 enum FwdBar { F_TH_FULL = 0, F_TH_EMPTY = 2, F_PH_FULL = 4, F_PH_EMPTY = 6, F_G_FULL = 8, F_G_EMPTY = 10, F_S_FULL = 12,
               F_S_EMPTY = 14, F_P_FULL = 16, F_P_EMPTY = 18, F_O_FULL = 20, F_O_EMPTY = 21, F_NBARS = 22 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_constant__ CUtensorMap tmPhi,
                 const __grid_constant__ CUtensorMap tmG, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -90,8 +102,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < F_NBARS; ++i) {
-      const bool four = (i == F_S_EMPTY || i == F_S_EMPTY + 1 || i == F_P_FULL || i == F_P_FULL + 1 || i == F_O_EMPTY);
-      mbar_init(&bars[i], four ? 4u : 1u);
+      const bool eight = (i == F_S_EMPTY || i == F_S_EMPTY + 1 || i == F_P_FULL || i == F_P_FULL + 1);
+      mbar_init(&bars[i], eight ? 8u : (i == F_O_EMPTY ? 4u : 1u));
     }
     fence_barrier_init();
   }
@@ -193,90 +205,103 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
       issue_pv(nc - 1, true);
     }
   } else {
-    const int q = warp & 3;
+    // eight softmax warps: warp w owns TMEM lanes 32 (w mod 4) .. and the 64-column half `hh` of every logits chunk
+    const int q = warp & 3, hh = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t taddr = lane_base + static_cast<uint32_t>(hh * 64);
+    float* xm = reinterpret_cast<float*>(smem + kFwdXch);  // [2][128] row maxima of the two halves
+    float* xl = xm + 256;                                  // [128] row sums of the upper half
     uint32_t tl = 0, si = 0, pi = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
       const int b = tile / p.q_tiles, q0 = (tile % p.q_tiles) * 128;
       const int64_t grow = static_cast<int64_t>(b) * p.Q + q0 + row;
-      float m = -INFINITY, l = 0.f;
-      for (int c = 0; c < nc; ++c) {  // pass 1: running maximum and sum of the row, log2 domain
+      float m = -INFINITY;
+      for (int c = 0; c < nc; ++c) {  // pass 1: row maximum
         const uint32_t sb = si & 1u;
         mbar_wait(&bars[F_S_FULL + sb], (si >> 1) & 1u);
         tc_fence_after();
-#pragma unroll 1
-        for (int blk = 0; blk < 4; ++blk) {
-          uint32_t r[32];
-          tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(blk * 32), r);
-          tmem_ld_wait();
-          float bm = -INFINITY;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + sb * 128u, r0);
+        tmem_ld32(taddr + sb * 128u + 32u, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[F_S_EMPTY + sb]);  // the values are in registers
+        float m0 = m, m1 = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) bm = fmaxf(bm, __uint_as_float(r[j]));
-          const float mn = fmaxf(m, bm * kLog2e);
-          float acc = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc += ex2(fmaf(__uint_as_float(r[j]), kLog2e, -mn));
-          l = fmaf(l, ex2(m - mn), acc);
-          m = mn;
+        for (int j = 0; j < 32; ++j) {
+          m0 = fmaxf(m0, __uint_as_float(r0[j]));
+          m1 = fmaxf(m1, __uint_as_float(r1[j]));
         }
+        m = fmaxf(m0, m1);
+        ++si;
+      }
+      xm[hh * 128 + row] = m;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m = fmaxf(m, xm[(hh ^ 1) * 128 + row]) * kLog2e;
+      float l = 0.f;
+      for (int c = 0; c < nc; ++c) {  // pass 2: exp2(s log2e - m) -> bf16 operand tile; row sum in float32
+        const uint32_t sb = si & 1u, pb = pi & 1u;
+        mbar_wait(&bars[F_S_FULL + sb], (si >> 1) & 1u);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + sb * 128u, r0);
+        tmem_ld32(taddr + sb * 128u + 32u, r1);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[F_S_EMPTY + sb]);
-        ++si;
-      }
-      const float lse = m + log2f(l);
-      if (p.lse2) p.lse2[grow] = lse;
-      __nv_bfloat16* prow = p.P ? p.P + grow * p.Kk : nullptr;
-      for (int c = 0; c < nc; ++c) {  // pass 2: normalised probabilities -> shared memory (-> global)
-        const uint32_t sb = si & 1u, pb = pi & 1u;
-        mbar_wait(&bars[F_S_FULL + sb], (si >> 1) & 1u);
-        mbar_wait(&bars[F_P_EMPTY + pb], ((pi >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-#pragma unroll 1
-        for (int blk = 0; blk < 4; ++blk) {
-          uint32_t r[32];
-          tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(blk * 32), r);
-          tmem_ld_wait();
-          uint32_t w[16];
+        uint32_t w0[16], w1[16];
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            w[j] = pack_bf16(ex2(fmaf(__uint_as_float(r[2 * j]), kLog2e, -lse)),
-                             ex2(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -lse)));
-          store_row_block(base + kFwdP + pb * 2u * kTile, row, blk, w);
-          if (prow) {
-            uint4* dst = reinterpret_cast<uint4*>(prow + c * 128 + blk * 32);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float a0 = ex2(fmaf(__uint_as_float(r0[2 * j]), kLog2e, -m));
+          const float a1 = ex2(fmaf(__uint_as_float(r0[2 * j + 1]), kLog2e, -m));
+          const float b0 = ex2(fmaf(__uint_as_float(r1[2 * j]), kLog2e, -m));
+          const float b1 = ex2(fmaf(__uint_as_float(r1[2 * j + 1]), kLog2e, -m));
+          l0 += a0 + a1;
+          l1 += b0 + b1;
+          w0[j] = pack_bf16(a0, a1);
+          w1[j] = pack_bf16(b0, b1);
         }
-        tc_fence_before();
+        l += l0 + l1;
+        mbar_wait(&bars[F_P_EMPTY + pb], ((pi >> 1) & 1u) ^ 1u);
+        store_row_block(base + kFwdP + pb * 2u * kTile, row, hh * 2, w0);
+        store_row_block(base + kFwdP + pb * 2u * kTile, row, hh * 2 + 1, w1);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bars[F_P_FULL + pb]);
-          mbar_arrive(&bars[F_S_EMPTY + sb]);
-        }
+        if (lane == 0) mbar_arrive(&bars[F_P_FULL + pb]);
         ++si;
         ++pi;
       }
-      mbar_wait(&bars[F_O_FULL], tl & 1u);
-      tc_fence_after();
-      __nv_bfloat16* orow = p.O + grow * p.dv;
-      for (int c0 = 0; c0 < p.dv; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + 256u + static_cast<uint32_t>(c0), r);
-        tmem_ld_wait();
-        uint32_t w[8];
+      if (hh == 1) {
+        xl[row] = l;
+        asm volatile("bar.arrive 2, 256;" ::: "memory");
+      } else {
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        l += xl[row];
+        if (p.lse2) p.lse2[grow] = m + log2f(l);
+        const float inv = 1.0f / l;
+        mbar_wait(&bars[F_O_FULL], tl & 1u);
+        tc_fence_after();
+        __nv_bfloat16* orow = p.O + grow * p.dv;
+        for (int c0 = 0; c0 < p.dv; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_base + 256u + static_cast<uint32_t>(c0), r);
+          tmem_ld_wait();
+          uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          for (int j = 0; j < 8; ++j)
+            w[j] = pack_bf16(inv * __uint_as_float(r[2 * j]), inv * __uint_as_float(r[2 * j + 1]));
+          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[F_O_EMPTY]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[F_O_EMPTY]);
     }
   }
   tc_fence_before();
@@ -446,7 +471,8 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
           }
         }
       }
-      __nv_bfloat16* dsrow = p.P + grow * p.Kk;
+      if (p.dsum) p.dsum[grow] = dsum;
+      __nv_bfloat16* dsrow = p.P ? p.P + grow * p.Kk : nullptr;
       for (int c = 0; c < nc; ++c) {
         const uint32_t sb = si & 1u;
         mbar_wait(&bars[Q_S_FULL + sb], (si >> 1) & 1u);
@@ -467,9 +493,11 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
             w[j] = pack_bf16(p0 * (__uint_as_float(g[2 * j]) - dsum), p1 * (__uint_as_float(g[2 * j + 1]) - dsum));
           }
           store_row_block(base + kBwdDS, row, blk, w);
-          uint4* dst = reinterpret_cast<uint4*>(dsrow + c * 128 + blk * 32);
+          if (dsrow) {
+            uint4* dst = reinterpret_cast<uint4*>(dsrow + c * 128 + blk * 32);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+            for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+          }
         }
         tc_fence_before();
         fence_proxy_async();
@@ -506,6 +534,224 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------- backward, key side
+// shared memory: phi_t | g_t (3 tiles) | stage[2] = {theta_h 8 KB, dO_h 3 x 8 KB, lse 256 B, dsum 256 B} | P^T[2] | dS^T[2]
+constexpr uint32_t kHalf = 8192u;  // 64 rows x 128 bytes
+constexpr uint32_t kKvPhi = 0, kKvG = kTile, kKvStage = 4 * kTile, kKvStageBytes = 4 * kHalf + 1024u,
+                   kKvPT = kKvStage + 2 * kKvStageBytes, kKvDST = kKvPT + 2 * kTile, kKvBars = kKvDST + 2 * kTile;
+constexpr uint32_t kKvSmem = kKvBars + 256u + 1024u;
+static_assert(kKvPT % 1024u == 0, "operand tiles must stay 1024-byte aligned");
+enum KvBar { K_KV_FULL = 0, K_KV_EMPTY = 1, K_ST_FULL = 2, K_ST_EMPTY = 4, K_SD_FULL = 6, K_SD_EMPTY = 8, K_PD_FULL = 10,
+             K_PD_EMPTY = 12, K_ACC_FULL = 14, K_ACC_EMPTY = 15, K_NBARS = 16 };
+// TMEM columns: S^T [0,64) [64,128), dP^T [128,192) [192,256), dg [256,448), dphi [448,512)
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_constant__ CUtensorMap tmPhi,
+                   const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmDOH,
+                   const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKvBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + K_NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < K_NBARS; ++i) {
+      const bool four = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_PD_FULL + 1 ||
+                         i == K_ACC_EMPTY);
+      mbar_init(&bars[i], four ? 4u : 1u);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ni = p.Q / 64;           // query half-tiles per walk
+  const int k_tiles = p.n_chunks;    // key tiles per sample
+  const int total = p.B * k_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmThetaH);
+      tma_prefetch_desc(&tmPhi);
+      tma_prefetch_desc(&tmG);
+      tma_prefetch_desc(&tmDOH);
+    }
+    uint32_t tl = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+      const int b = tile / k_tiles, k0 = (tile % k_tiles) * 128;
+      mbar_wait(&bars[K_KV_EMPTY], (tl & 1u) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&bars[K_KV_FULL], static_cast<uint32_t>(1 + p.v_boxes) * kTile);
+        tma_load_3d(smem + kKvPhi, &tmPhi, &bars[K_KV_FULL], 0, k0, b);
+        for (int j = 0; j < p.v_boxes; ++j) tma_load_3d(smem + kKvG + j * kTile, &tmG, &bars[K_KV_FULL], j * 64, k0, b);
+      }
+      __syncwarp();
+      for (int i = 0; i < ni; ++i, ++it) {
+        const uint32_t slot = it & 1u;
+        mbar_wait(&bars[K_ST_EMPTY + slot], ((it >> 1) & 1u) ^ 1u);
+        if (elect_one_sync()) {
+          uint8_t* st = smem + kKvStage + slot * kKvStageBytes;
+          uint64_t* bar = &bars[K_ST_FULL + slot];
+          mbar_expect_tx(bar, static_cast<uint32_t>(1 + p.v_boxes) * kHalf + 512u);
+          tma_load_3d(st, &tmThetaH, bar, 0, i * 64, b);
+          for (int j = 0; j < p.v_boxes; ++j) tma_load_3d(st + (1 + j) * kHalf, &tmDOH, bar, j * 64, i * 64, b);
+          const int64_t qoff = static_cast<int64_t>(b) * p.Q + i * 64;
+          bulk_load_1d(st + 4 * kHalf, p.lse2 + qoff, 256u, bar);
+          bulk_load_1d(st + 4 * kHalf + 256u, p.dsum + qoff, 256u, bar);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t tl = 0, it = 0, ia = 0;  // it: next S^T/dP^T product, ia: next accumulation (both count query half-tiles)
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+      mbar_wait(&bars[K_KV_FULL], tl & 1u);
+      const uint64_t da_phi = umma_desc_kmajor(base + kKvPhi, 128);
+      // dg += P^T_j dO_j,  dphi += dS^T_j theta_j  for query half-tile j of this walk
+      auto issue_acc = [&](int j, bool last) {
+        const uint32_t slot = ia & 1u, pb = ia & 1u;
+        mbar_wait(&bars[K_PD_FULL + pb], (ia >> 1) & 1u);
+        if (j == 0) mbar_wait(&bars[K_ACC_EMPTY], (tl & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t st = base + kKvStage + slot * kKvStageBytes;
+          const uint64_t db_do = desc_mn(st + kHalf, kHalf), db_th = desc_mn(st, kHalf);
+          const uint64_t da_p = umma_desc_kmajor(base + kKvPT + pb * kTile, 128);
+          const uint64_t da_ds = umma_desc_kmajor(base + kKvDST + pb * kTile, 128);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + 256u, da_p + 2u * ks, db_do + 128u * ks, p.idesc_o, (j | ks) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + 448u, da_ds + 2u * ks, db_th + 128u * ks, p.idesc_dq, (j | ks) != 0 ? 1u : 0u);
+          umma_commit(&bars[K_PD_EMPTY + pb]);
+          umma_commit(&bars[K_ST_EMPTY + slot]);
+          if (last) umma_commit(&bars[K_ACC_FULL]);
+        }
+        __syncwarp();
+        ++ia;
+      };
+      for (int i = 0; i < ni; ++i, ++it) {
+        const uint32_t slot = it & 1u, sb = it & 1u;
+        mbar_wait(&bars[K_ST_FULL + slot], (it >> 1) & 1u);
+        mbar_wait(&bars[K_SD_EMPTY + sb], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t st = base + kKvStage + slot * kKvStageBytes;
+          const uint64_t db_th = umma_desc_kmajor(st, 128);
+          for (int k = 0; k < p.d_steps; ++k)
+            umma_bf16(tmem_base + sb * 64u, da_phi + 2u * k, db_th + 2u * k, p.idesc_s64, k != 0 ? 1u : 0u);
+          for (int ks = 0; ks < p.dv_steps; ++ks) {
+            const uint64_t da = umma_desc_kmajor(base + kKvG + static_cast<uint32_t>(ks >> 2) * kTile, 128) + 2u * (ks & 3);
+            const uint64_t db = umma_desc_kmajor(st + kHalf + static_cast<uint32_t>(ks >> 2) * kHalf, 128) + 2u * (ks & 3);
+            umma_bf16(tmem_base + 128u + sb * 64u, da, db, p.idesc_s64, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars[K_SD_FULL + sb]);
+          if (i == ni - 1) umma_commit(&bars[K_KV_EMPTY]);  // phi_t and g_t have no reader after these products
+        }
+        __syncwarp();
+        if (i > 0) issue_acc(i - 1, false);
+      }
+      issue_acc(ni - 1, true);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // key row of the tile
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t tl = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+      const int b = tile / k_tiles, k0 = (tile % k_tiles) * 128;
+      for (int i = 0; i < ni; ++i, ++it) {
+        const uint32_t slot = it & 1u, sb = it & 1u;
+        mbar_wait(&bars[K_ST_FULL + slot], (it >> 1) & 1u);   // lse / dsum of these 64 queries
+        mbar_wait(&bars[K_SD_FULL + sb], (it >> 1) & 1u);
+        mbar_wait(&bars[K_PD_EMPTY + sb], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const float4* lse4 = reinterpret_cast<const float4*>(smem + kKvStage + slot * kKvStageBytes + 4 * kHalf);
+        const float4* dsm4 = lse4 + 16;
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+          uint32_t r[32], g[32];
+          tmem_ld32(taddr + sb * 64u + static_cast<uint32_t>(blk * 32), r);
+          tmem_ld32(taddr + 128u + sb * 64u + static_cast<uint32_t>(blk * 32), g);
+          tmem_ld_wait();
+          uint32_t wp[16], wd[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 ls = lse4[blk * 8 + j4], dm = dsm4[blk * 8 + j4];
+            const float p0 = ex2(fmaf(__uint_as_float(r[4 * j4]), kLog2e, -ls.x));
+            const float p1 = ex2(fmaf(__uint_as_float(r[4 * j4 + 1]), kLog2e, -ls.y));
+            const float p2 = ex2(fmaf(__uint_as_float(r[4 * j4 + 2]), kLog2e, -ls.z));
+            const float p3 = ex2(fmaf(__uint_as_float(r[4 * j4 + 3]), kLog2e, -ls.w));
+            wp[2 * j4] = pack_bf16(p0, p1);
+            wp[2 * j4 + 1] = pack_bf16(p2, p3);
+            wd[2 * j4] = pack_bf16(p0 * (__uint_as_float(g[4 * j4]) - dm.x), p1 * (__uint_as_float(g[4 * j4 + 1]) - dm.y));
+            wd[2 * j4 + 1] =
+                pack_bf16(p2 * (__uint_as_float(g[4 * j4 + 2]) - dm.z), p3 * (__uint_as_float(g[4 * j4 + 3]) - dm.w));
+          }
+          store_row_block(base + kKvPT + sb * kTile, row, blk, wp);
+          store_row_block(base + kKvDST + sb * kTile, row, blk, wd);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars[K_PD_FULL + sb]);
+          mbar_arrive(&bars[K_SD_EMPTY + sb]);
+        }
+      }
+      mbar_wait(&bars[K_ACC_FULL], tl & 1u);
+      tc_fence_after();
+      const int64_t krow = static_cast<int64_t>(b) * p.Kk + k0 + row;
+      __nv_bfloat16* grow_ = p.dG + krow * p.dv;
+      for (int c0 = 0; c0 < p.dv; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + 256u + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        uint4* dst = reinterpret_cast<uint4*>(grow_ + c0);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      __nv_bfloat16* prow = p.dPhi + krow * p.d;
+      for (int c0 = 0; c0 < p.d; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + 448u + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        uint4* dst = reinterpret_cast<uint4*>(prow + c0);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (c0 + 8 < p.d) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[K_ACC_EMPTY]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 int fill_params(AttnParams* p, int B, int Q, int Kk, int d, int dv, const char* who) {
   ICGAN_REQUIRE(B > 0 && Q > 0 && Kk > 0 && Q % 128 == 0 && Kk % 128 == 0,
                 "%s: Q (%d) and Kk (%d) must be multiples of 128", who, Q, Kk);
@@ -521,6 +767,7 @@ int fill_params(AttnParams* p, int B, int Q, int Kk, int d, int dv, const char* 
   p->idesc_s = umma_idesc_bf16(128, 128);
   p->idesc_o = umma_idesc_bf16(128, static_cast<uint32_t>(dv)) | (1u << 16);
   p->idesc_dq = umma_idesc_bf16(128, static_cast<uint32_t>(p->d_steps * 16)) | (1u << 16);
+  p->idesc_s64 = umma_idesc_bf16(128, 64);
   return 0;
 }
 
@@ -529,13 +776,12 @@ int fill_params(AttnParams* p, int B, int Q, int Kk, int d, int dv, const char* 
 
 using namespace icgan;
 
-extern "C" int icgan_attn_fwd(const void* theta, const void* phi, const void* g, void* o, void* probs, float* lse2,
-                              int B, int Q, int Kk, int d, int dv, void* stream) {
+extern "C" int icgan_attn_fwd(const void* theta, const void* phi, const void* g, void* o, float* lse2, int B, int Q,
+                              int Kk, int d, int dv, void* stream) {
   ICGAN_REQUIRE(theta && phi && g && o, "icgan_attn_fwd: null pointer");
   AttnParams p{};
   if (int rc = fill_params(&p, B, Q, Kk, d, dv, "icgan_attn_fwd")) return rc;
   p.O = static_cast<__nv_bfloat16*>(o);
-  p.P = static_cast<__nv_bfloat16*>(probs);
   p.lse2 = lse2;
   CUtensorMap tmT, tmP, tmG;
   if (int rc = make_map3(&tmT, theta, d, Q, B, d, static_cast<uint64_t>(Q) * d, 64, 128)) return rc;
@@ -545,15 +791,15 @@ extern "C" int icgan_attn_fwd(const void* theta, const void* phi, const void* g,
   if (first_use_on_this_device(&configured))
     ICGAN_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, p);
+  attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, p);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int icgan_attn_bwd_q(const void* theta, const void* phi, const void* g, const void* o, const void* dout,
-                                const float* lse2, void* dtheta, void* ds, int B, int Q, int Kk, int d, int dv,
-                                void* stream) {
-  ICGAN_REQUIRE(theta && phi && g && o && dout && lse2 && dtheta && ds, "icgan_attn_bwd_q: null pointer");
+                                const float* lse2, void* dtheta, void* ds, float* dsum, int B, int Q, int Kk, int d,
+                                int dv, void* stream) {
+  ICGAN_REQUIRE(theta && phi && g && o && dout && lse2 && dtheta, "icgan_attn_bwd_q: null pointer");
   AttnParams p{};
   if (int rc = fill_params(&p, B, Q, Kk, d, dv, "icgan_attn_bwd_q")) return rc;
   p.O_in = static_cast<const __nv_bfloat16*>(o);
@@ -561,6 +807,7 @@ extern "C" int icgan_attn_bwd_q(const void* theta, const void* phi, const void* 
   p.P = static_cast<__nv_bfloat16*>(ds);
   p.dTheta = static_cast<__nv_bfloat16*>(dtheta);
   p.lse2 = const_cast<float*>(lse2);
+  p.dsum = dsum;
   CUtensorMap tmT, tmP, tmG, tmD;
   if (int rc = make_map3(&tmT, theta, d, Q, B, d, static_cast<uint64_t>(Q) * d, 64, 128)) return rc;
   if (int rc = make_map3(&tmP, phi, d, Kk, B, d, static_cast<uint64_t>(Kk) * d, 64, 128)) return rc;
@@ -571,6 +818,31 @@ extern "C" int icgan_attn_bwd_q(const void* theta, const void* phi, const void* 
     ICGAN_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   attn_bwd_q_kernel<<<grid, kAttnThreads, kBwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, tmD, p);
+  ICGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int icgan_attn_bwd_kv(const void* theta, const void* phi, const void* g, const void* dout, const float* lse2,
+                                 const float* dsum, void* dphi, void* dg, int B, int Q, int Kk, int d, int dv,
+                                 void* stream) {
+  ICGAN_REQUIRE(theta && phi && g && dout && lse2 && dsum && dphi && dg, "icgan_attn_bwd_kv: null pointer");
+  AttnParams p{};
+  if (int rc = fill_params(&p, B, Q, Kk, d, dv, "icgan_attn_bwd_kv")) return rc;
+  p.lse2 = const_cast<float*>(lse2);
+  p.dsum = const_cast<float*>(dsum);
+  p.dPhi = static_cast<__nv_bfloat16*>(dphi);
+  p.dG = static_cast<__nv_bfloat16*>(dg);
+  CUtensorMap tmT, tmP, tmG, tmD;
+  if (int rc = make_map3(&tmT, theta, d, Q, B, d, static_cast<uint64_t>(Q) * d, 64, 64)) return rc;
+  if (int rc = make_map3(&tmP, phi, d, Kk, B, d, static_cast<uint64_t>(Kk) * d, 64, 128)) return rc;
+  if (int rc = make_map3(&tmG, g, dv, Kk, B, dv, static_cast<uint64_t>(Kk) * dv, 64, 128)) return rc;
+  if (int rc = make_map3(&tmD, dout, dv, Q, B, dv, static_cast<uint64_t>(Q) * dv, 64, 64)) return rc;
+  static unsigned long long configured = 0ull;
+  if (first_use_on_this_device(&configured))
+    ICGAN_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
+  const int total = B * p.n_chunks;
+  const int grid = total < num_sms() ? total : num_sms();
+  attn_bwd_kv_kernel<<<grid, kAttnThreads, kKvSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, tmD, p);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -883,13 +883,11 @@ class AttentionCoreFn(torch.autograd.Function):
         if ctx.fused:  # logits live in tensor memory only (csrc/tc_attn.cu)
             o = torch.empty(B, Q, dv, device=theta.device, dtype=theta.dtype)
             grad = any(ctx.needs_input_grad)
-            P = torch.empty(B, Q, Kk, device=theta.device, dtype=theta.dtype) if grad else None
             lse = torch.empty(B, Q, device=theta.device, dtype=torch.float32) if grad else None
-            call("icgan_attn_fwd", ptr(theta), ptr(phi), ptr(g), ptr(o), ptr(P), ptr(lse), B, Q, Kk, d, dv,
-                 stream_ptr())
+            call("icgan_attn_fwd", ptr(theta), ptr(phi), ptr(g), ptr(o), ptr(lse), B, Q, Kk, d, dv, stream_ptr())
             ctx.tc = True
             if grad:
-                ctx.save_for_backward(theta, phi, g, P, o, lse)
+                ctx.save_for_backward(theta, phi, g, o, lse)
             return o
         S = torch.empty(B, Q, Kk, device=theta.device, dtype=torch.float32)
         if tc:
@@ -912,15 +910,15 @@ class AttentionCoreFn(torch.autograd.Function):
     def backward(ctx, do):
         do = do.contiguous()
         if ctx.fused:
-            theta, phi, g, P, o, lse = ctx.saved_tensors
+            theta, phi, g, o, lse = ctx.saved_tensors
             B, Q, d = theta.shape
             Kk, dv = phi.shape[1], g.shape[2]
             dtheta, dphi, dg = torch.empty_like(theta), torch.empty_like(phi), torch.empty_like(g)
-            dS = torch.empty_like(P)
-            call("icgan_attn_bwd_q", ptr(theta), ptr(phi), ptr(g), ptr(o), ptr(do), ptr(lse), ptr(dtheta), ptr(dS),
+            dsum = torch.empty_like(lse)
+            call("icgan_attn_bwd_q", ptr(theta), ptr(phi), ptr(g), ptr(o), ptr(do), ptr(lse), ptr(dtheta), None,
+                 ptr(dsum), B, Q, Kk, d, dv, stream_ptr())
+            call("icgan_attn_bwd_kv", ptr(theta), ptr(phi), ptr(g), ptr(do), ptr(lse), ptr(dsum), ptr(dphi), ptr(dg),
                  B, Q, Kk, d, dv, stream_ptr())
-            _gemm_tc(P, do, dg, Kk, dv, Q, B, 1, 1, Kk, Q * Kk, dv, Q * dv, dv, Kk * dv)
-            _gemm_tc(dS, theta, dphi, Kk, d, Q, B, 1, 1, Kk, Q * Kk, d, Q * d, d, Kk * d)
             return dtheta, dphi, dg
         theta, phi, g, P = ctx.saved_tensors
         B, Q, d = theta.shape

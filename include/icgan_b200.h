@@ -211,15 +211,20 @@ int icgan_gemm_tc(const void* A, const void* B, void* C, int M, int N, int K, in
 
 /* Fused non-local block core (layers.Attention.forward, BigGAN_PyTorch/layers.py:233-243: beta = softmax(theta^T phi),
  * o = g beta^T) on tcgen05, bf16 operands: theta [B,Q,d], phi [B,Kk,d], g [B,Kk,dv], o [B,Q,dv]; Q and Kk multiples of
- * 128, d a multiple of 8 in [8,64], dv a multiple of 16 in [16,192].  The logits stay in tensor memory.
- * probs (nullable): the bf16 probabilities [B,Q,Kk], stored for the backward (dg = probs^T dout);
- * lse2 (nullable): per-row log2-sum-exp2 of the logits * log2(e), float32 [B,Q]. */
-int icgan_attn_fwd(const void* theta, const void* phi, const void* g, void* o, void* probs, float* lse2, int B, int Q,
-                   int Kk, int d, int dv, void* stream);
+ * 128, d a multiple of 8 in [8,64], dv a multiple of 16 in [16,192].  The logits and probabilities stay on the SM.
+ * lse2 (nullable): per-row log2-sum-exp2 of the logits * log2(e), float32 [B,Q], what the backward restarts from. */
+int icgan_attn_fwd(const void* theta, const void* phi, const void* g, void* o, float* lse2, int B, int Q, int Kk, int d,
+                   int dv, void* stream);
 /* Query side of its backward: recomputes the probabilities from lse2, forms dP = dout g^T in tensor memory,
- * ds = probs * (dP - rowsum(dout * o)) -> bf16 [B,Q,Kk] (operand of dphi = ds^T theta) and dtheta = ds phi [B,Q,d]. */
+ * ds = probs * (dP - rowsum(dout * o)) and dtheta = ds phi [B,Q,d].  ds (nullable): the bf16 [B,Q,Kk] copy of ds;
+ * dsum (nullable): rowsum(dout * o), float32 [B,Q], the input of the key side. */
 int icgan_attn_bwd_q(const void* theta, const void* phi, const void* g, const void* o, const void* dout,
-                     const float* lse2, void* dtheta, void* ds, int B, int Q, int Kk, int d, int dv, void* stream);
+                     const float* lse2, void* dtheta, void* ds, float* dsum, int B, int Q, int Kk, int d, int dv,
+                     void* stream);
+/* Key side: dphi = ds^T theta [B,Kk,d] and dg = probs^T dout [B,Kk,dv], with probs and ds rebuilt 128 keys x 64 queries
+ * at a time in tensor / shared memory from lse2 and dsum. */
+int icgan_attn_bwd_kv(const void* theta, const void* phi, const void* g, const void* dout, const float* lse2,
+                      const float* dsum, void* dphi, void* dg, int B, int Q, int Kk, int d, int dv, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * k-NN conditioning build (replaces faiss.IndexFlatL2.add/search in ILSVRC_HDF5_feats._obtain_nns,
