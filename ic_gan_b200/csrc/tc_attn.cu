@@ -133,8 +133,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
         tma_load_3d(smem + kFwdTheta + tb * kTile, &tmTheta, &bars[F_TH_FULL + tb], 0, q0, b);
       }
       __syncwarp();
-      for (int item = 0; item < 2 * nc; ++item) {
-        const int c = item < nc ? item : item - nc;
+      // pass 1 (row maxima) needs phi only and g's ring would sit idle: its two 3-tile slots carry the phi chunks three
+      // at a time, so up to six chunk loads are in flight instead of the phi ring's two
+      for (int c0 = 0; c0 < nc; c0 += 3) {
+        const uint32_t gs = gi & 1u;
+        const int n = nc - c0 < 3 ? nc - c0 : 3;
+        mbar_wait(&bars[F_G_EMPTY + gs], ((gi >> 1) & 1u) ^ 1u);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars[F_G_FULL + gs], static_cast<uint32_t>(n) * kTile);
+          for (int j = 0; j < n; ++j)
+            tma_load_3d(smem + kFwdG + (gs * 3u + j) * kTile, &tmPhi, &bars[F_G_FULL + gs], 0, (c0 + j) * 128, b);
+        }
+        __syncwarp();
+        ++gi;
+      }
+      for (int c = 0; c < nc; ++c) {  // pass 2: phi chunk -> phi ring, g chunk -> g ring
         const uint32_t slot = fi & 1u;
         mbar_wait(&bars[F_PH_EMPTY + slot], ((fi >> 1) & 1u) ^ 1u);
         if (elect_one_sync()) {
@@ -143,17 +156,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
         }
         __syncwarp();
         ++fi;
-        if (item >= nc) {
-          const uint32_t gs = gi & 1u;
-          mbar_wait(&bars[F_G_EMPTY + gs], ((gi >> 1) & 1u) ^ 1u);
-          if (elect_one_sync()) {
-            mbar_expect_tx(&bars[F_G_FULL + gs], static_cast<uint32_t>(p.v_boxes) * kTile);
-            for (int j = 0; j < p.v_boxes; ++j)
-              tma_load_3d(smem + kFwdG + (gs * 3u + j) * kTile, &tmG, &bars[F_G_FULL + gs], j * 64, c * 128, b);
-          }
-          __syncwarp();
-          ++gi;
+        const uint32_t gs = gi & 1u;
+        mbar_wait(&bars[F_G_EMPTY + gs], ((gi >> 1) & 1u) ^ 1u);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars[F_G_FULL + gs], static_cast<uint32_t>(p.v_boxes) * kTile);
+          for (int j = 0; j < p.v_boxes; ++j)
+            tma_load_3d(smem + kFwdG + (gs * 3u + j) * kTile, &tmG, &bars[F_G_FULL + gs], j * 64, c * 128, b);
         }
+        __syncwarp();
+        ++gi;
       }
     }
   } else if (warp == 1) {
@@ -184,7 +195,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
         ++gi;
         ++pi;
       };
-      for (int item = 0; item < 2 * nc; ++item) {
+      for (int c0 = 0; c0 < nc; c0 += 3) {  // pass 1: logits from the phi chunks parked in g's ring
+        const uint32_t gs = gi & 1u;
+        const int n = nc - c0 < 3 ? nc - c0 : 3;
+        mbar_wait(&bars[F_G_FULL + gs], (gi >> 1) & 1u);
+        for (int j = 0; j < n; ++j) {
+          const uint32_t sb = si & 1u;
+          mbar_wait(&bars[F_S_EMPTY + sb], ((si >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint64_t db = umma_desc_kmajor(base + kFwdG + (gs * 3u + j) * kTile, 128);
+            for (int k = 0; k < p.d_steps; ++k)
+              umma_bf16(tmem_base + sb * 128u, da + 2u * k, db + 2u * k, p.idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&bars[F_S_FULL + sb]);
+            if (j == n - 1) umma_commit(&bars[F_G_EMPTY + gs]);
+          }
+          __syncwarp();
+          ++si;
+        }
+        ++gi;
+      }
+      for (int c = 0; c < nc; ++c) {  // pass 2
         const uint32_t slot = fi & 1u, sb = si & 1u;
         mbar_wait(&bars[F_PH_FULL + slot], (fi >> 1) & 1u);
         mbar_wait(&bars[F_S_EMPTY + sb], ((si >> 1) & 1u) ^ 1u);
@@ -195,12 +226,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
             umma_bf16(tmem_base + sb * 128u, da + 2u * k, db + 2u * k, p.idesc_s, k != 0 ? 1u : 0u);
           umma_commit(&bars[F_PH_EMPTY + slot]);
           umma_commit(&bars[F_S_FULL + sb]);
-          if (item == 2 * nc - 1) umma_commit(&bars[F_TH_EMPTY + tb]);
+          if (c == nc - 1) umma_commit(&bars[F_TH_EMPTY + tb]);
         }
         __syncwarp();
         ++fi;
         ++si;
-        if (item > nc) issue_pv(item - 1 - nc, false);
+        if (c > 0) issue_pv(c - 1, false);
       }
       issue_pv(nc - 1, true);
     }
@@ -310,13 +341,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------- backward, query side
-// shared memory: theta | dO (3 tiles) | phi[2] | g (3 tiles) | dS (2 tiles) | barriers
-constexpr uint32_t kBwdTheta = 0, kBwdDO = kTile, kBwdPhi = 4 * kTile, kBwdG = 6 * kTile, kBwdDS = 9 * kTile,
-                   kBwdBars = 11 * kTile;
+// shared memory: theta | dO (3 tiles) | phi[2] | g[2] (3 tiles each) | dS (2 tiles) | barriers
+constexpr uint32_t kBwdTheta = 0, kBwdDO = kTile, kBwdPhi = 4 * kTile, kBwdG = 6 * kTile, kBwdDS = 12 * kTile,
+                   kBwdBars = 14 * kTile;
 constexpr uint32_t kBwdSmem = kBwdBars + 256u + 1024u;
-enum BwdBar { Q_TD_FULL = 0, Q_TD_EMPTY = 1, Q_PH_FULL = 2, Q_PH_EMPTY = 4, Q_G_FULL = 6, Q_G_EMPTY = 7, Q_S_FULL = 8,
-              Q_S_EMPTY = 10, Q_DP_FULL = 12, Q_DP_EMPTY = 13, Q_DS_FULL = 14, Q_DS_EMPTY = 15, Q_DT_FULL = 16,
-              Q_DT_EMPTY = 17, Q_NBARS = 18 };
+enum BwdBar { Q_TD_FULL = 0, Q_TD_EMPTY = 1, Q_PH_FULL = 2, Q_PH_EMPTY = 4, Q_G_FULL = 6, Q_G_EMPTY = 8, Q_S_FULL = 10,
+              Q_S_EMPTY = 12, Q_DP_FULL = 14, Q_DP_EMPTY = 15, Q_DS_FULL = 16, Q_DS_EMPTY = 17, Q_DT_FULL = 18,
+              Q_DT_EMPTY = 19, Q_NBARS = 20 };
 // TMEM columns: logits [0,128) and [128,256), dP [256,384), dtheta [384,448)
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -375,11 +406,12 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
         }
         __syncwarp();
         ++fi;
-        mbar_wait(&bars[Q_G_EMPTY], (gi & 1u) ^ 1u);
+        const uint32_t gs = gi & 1u;
+        mbar_wait(&bars[Q_G_EMPTY + gs], ((gi >> 1) & 1u) ^ 1u);
         if (elect_one_sync()) {
-          mbar_expect_tx(&bars[Q_G_FULL], static_cast<uint32_t>(p.v_boxes) * kTile);
+          mbar_expect_tx(&bars[Q_G_FULL + gs], static_cast<uint32_t>(p.v_boxes) * kTile);
           for (int j = 0; j < p.v_boxes; ++j)
-            tma_load_3d(smem + kBwdG + j * kTile, &tmG, &bars[Q_G_FULL], j * 64, c * 128, b);
+            tma_load_3d(smem + kBwdG + (gs * 3u + j) * kTile, &tmG, &bars[Q_G_FULL + gs], j * 64, c * 128, b);
         }
         __syncwarp();
         ++gi;
@@ -426,17 +458,18 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
         __syncwarp();
         ++fi;
         ++si;
-        mbar_wait(&bars[Q_G_FULL], gi & 1u);
+        const uint32_t gs = gi & 1u;
+        mbar_wait(&bars[Q_G_FULL + gs], (gi >> 1) & 1u);
         mbar_wait(&bars[Q_DP_EMPTY], (gi & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one_sync()) {
           for (int ks = 0; ks < p.dv_steps; ++ks) {
             const uint32_t off = static_cast<uint32_t>(ks >> 2) * kTile;
             const uint64_t da = umma_desc_kmajor(base + kBwdDO + off, 128) + 2u * (ks & 3);
-            const uint64_t db = umma_desc_kmajor(base + kBwdG + off, 128) + 2u * (ks & 3);
+            const uint64_t db = umma_desc_kmajor(base + kBwdG + gs * 3u * kTile + off, 128) + 2u * (ks & 3);
             umma_bf16(tmem_base + 256u, da, db, p.idesc_s, ks != 0 ? 1u : 0u);
           }
-          umma_commit(&bars[Q_G_EMPTY]);
+          umma_commit(&bars[Q_G_EMPTY + gs]);
           umma_commit(&bars[Q_DP_FULL]);
           if (c == nc - 1) umma_commit(&bars[Q_TD_EMPTY]);  // theta and dO have no reader after this product
         }
@@ -535,14 +568,14 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------- backward, key side
-// shared memory: phi_t | g_t (3 tiles) | stage[2] = {theta_h 8 KB, dO_h 3 x 8 KB, lse 256 B, dsum 256 B} | P^T[2] | dS^T[2]
+// shared memory: phi_t | g_t (3 tiles) | stage[3] = {theta_h 8 KB, dO_h 3 x 8 KB, lse 256 B, dsum 256 B} | P^T | dS^T
 constexpr uint32_t kHalf = 8192u;  // 64 rows x 128 bytes
 constexpr uint32_t kKvPhi = 0, kKvG = kTile, kKvStage = 4 * kTile, kKvStageBytes = 4 * kHalf + 1024u,
-                   kKvPT = kKvStage + 2 * kKvStageBytes, kKvDST = kKvPT + 2 * kTile, kKvBars = kKvDST + 2 * kTile;
+                   kKvPT = kKvStage + 3 * kKvStageBytes, kKvDST = kKvPT + kTile, kKvBars = kKvDST + kTile;
 constexpr uint32_t kKvSmem = kKvBars + 256u + 1024u;
 static_assert(kKvPT % 1024u == 0, "operand tiles must stay 1024-byte aligned");
-enum KvBar { K_KV_FULL = 0, K_KV_EMPTY = 1, K_ST_FULL = 2, K_ST_EMPTY = 4, K_SD_FULL = 6, K_SD_EMPTY = 8, K_PD_FULL = 10,
-             K_PD_EMPTY = 12, K_ACC_FULL = 14, K_ACC_EMPTY = 15, K_NBARS = 16 };
+enum KvBar { K_KV_FULL = 0, K_KV_EMPTY = 1, K_ST_FULL = 2, K_ST_EMPTY = 5, K_SD_FULL = 8, K_SD_EMPTY = 10, K_PD_FULL = 12,
+             K_PD_EMPTY = 13, K_ACC_FULL = 14, K_ACC_EMPTY = 15, K_NBARS = 16 };
 // TMEM columns: S^T [0,64) [64,128), dP^T [128,192) [192,256), dg [256,448), dphi [448,512)
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -566,8 +599,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < K_NBARS; ++i) {
-      const bool four = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_PD_FULL + 1 ||
-                         i == K_ACC_EMPTY);
+      const bool four = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_ACC_EMPTY);
       mbar_init(&bars[i], four ? 4u : 1u);
     }
     fence_barrier_init();
@@ -591,7 +623,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
       tma_prefetch_desc(&tmG);
       tma_prefetch_desc(&tmDOH);
     }
-    uint32_t tl = 0, it = 0;
+    uint32_t tl = 0, slot = 0, sph = 0;  // stage ring position and phase
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
       const int b = tile / k_tiles, k0 = (tile % k_tiles) * 128;
       mbar_wait(&bars[K_KV_EMPTY], (tl & 1u) ^ 1u);
@@ -601,9 +633,8 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
         for (int j = 0; j < p.v_boxes; ++j) tma_load_3d(smem + kKvG + j * kTile, &tmG, &bars[K_KV_FULL], j * 64, k0, b);
       }
       __syncwarp();
-      for (int i = 0; i < ni; ++i, ++it) {
-        const uint32_t slot = it & 1u;
-        mbar_wait(&bars[K_ST_EMPTY + slot], ((it >> 1) & 1u) ^ 1u);
+      for (int i = 0; i < ni; ++i) {
+        mbar_wait(&bars[K_ST_EMPTY + slot], sph ^ 1u);
         if (elect_one_sync()) {
           uint8_t* st = smem + kKvStage + slot * kKvStageBytes;
           uint64_t* bar = &bars[K_ST_FULL + slot];
@@ -615,40 +646,45 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
           bulk_load_1d(st + 4 * kHalf + 256u, p.dsum + qoff, 256u, bar);
         }
         __syncwarp();
+        if (++slot == 3u) {
+          slot = 0;
+          sph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
     uint32_t tl = 0, it = 0, ia = 0;  // it: next S^T/dP^T product, ia: next accumulation (both count query half-tiles)
+    uint32_t slot = 0, sph = 0, aslot = 0;  // stage ring position / phase of `it`, position of `ia`
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
       mbar_wait(&bars[K_KV_FULL], tl & 1u);
       const uint64_t da_phi = umma_desc_kmajor(base + kKvPhi, 128);
       // dg += P^T_j dO_j,  dphi += dS^T_j theta_j  for query half-tile j of this walk
       auto issue_acc = [&](int j, bool last) {
-        const uint32_t slot = ia & 1u, pb = ia & 1u;
-        mbar_wait(&bars[K_PD_FULL + pb], (ia >> 1) & 1u);
+        mbar_wait(&bars[K_PD_FULL], ia & 1u);
         if (j == 0) mbar_wait(&bars[K_ACC_EMPTY], (tl & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t st = base + kKvStage + slot * kKvStageBytes;
+          const uint32_t st = base + kKvStage + aslot * kKvStageBytes;
           const uint64_t db_do = desc_mn(st + kHalf, kHalf), db_th = desc_mn(st, kHalf);
-          const uint64_t da_p = umma_desc_kmajor(base + kKvPT + pb * kTile, 128);
-          const uint64_t da_ds = umma_desc_kmajor(base + kKvDST + pb * kTile, 128);
+          const uint64_t da_p = umma_desc_kmajor(base + kKvPT, 128);
+          const uint64_t da_ds = umma_desc_kmajor(base + kKvDST, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_bf16(tmem_base + 256u, da_p + 2u * ks, db_do + 128u * ks, p.idesc_o, (j | ks) != 0 ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_bf16(tmem_base + 448u, da_ds + 2u * ks, db_th + 128u * ks, p.idesc_dq, (j | ks) != 0 ? 1u : 0u);
-          umma_commit(&bars[K_PD_EMPTY + pb]);
-          umma_commit(&bars[K_ST_EMPTY + slot]);
+          umma_commit(&bars[K_PD_EMPTY]);
+          umma_commit(&bars[K_ST_EMPTY + aslot]);
           if (last) umma_commit(&bars[K_ACC_FULL]);
         }
         __syncwarp();
         ++ia;
+        if (++aslot == 3u) aslot = 0;
       };
       for (int i = 0; i < ni; ++i, ++it) {
-        const uint32_t slot = it & 1u, sb = it & 1u;
-        mbar_wait(&bars[K_ST_FULL + slot], (it >> 1) & 1u);
+        const uint32_t sb = it & 1u;
+        mbar_wait(&bars[K_ST_FULL + slot], sph);
         mbar_wait(&bars[K_SD_EMPTY + sb], ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one_sync()) {
@@ -665,6 +701,10 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
           if (i == ni - 1) umma_commit(&bars[K_KV_EMPTY]);  // phi_t and g_t have no reader after these products
         }
         __syncwarp();
+        if (++slot == 3u) {
+          slot = 0;
+          sph ^= 1u;
+        }
         if (i > 0) issue_acc(i - 1, false);
       }
       issue_acc(ni - 1, true);
@@ -673,24 +713,23 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
     const int q = warp & 3;
     const int row = q * 32 + lane;  // key row of the tile
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t tl = 0, it = 0;
+    uint32_t tl = 0, it = 0, slot = 0, sph = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
       const int b = tile / k_tiles, k0 = (tile % k_tiles) * 128;
       for (int i = 0; i < ni; ++i, ++it) {
-        const uint32_t slot = it & 1u, sb = it & 1u;
-        mbar_wait(&bars[K_ST_FULL + slot], (it >> 1) & 1u);   // lse / dsum of these 64 queries
+        const uint32_t sb = it & 1u;
+        mbar_wait(&bars[K_ST_FULL + slot], sph);   // lse / dsum of these 64 queries
         mbar_wait(&bars[K_SD_FULL + sb], (it >> 1) & 1u);
-        mbar_wait(&bars[K_PD_EMPTY + sb], ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const float4* lse4 = reinterpret_cast<const float4*>(smem + kKvStage + slot * kKvStageBytes + 4 * kHalf);
         const float4* dsm4 = lse4 + 16;
-#pragma unroll 1
+        uint32_t wp[2][16], wd[2][16];
+#pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
           uint32_t r[32], g[32];
           tmem_ld32(taddr + sb * 64u + static_cast<uint32_t>(blk * 32), r);
           tmem_ld32(taddr + 128u + sb * 64u + static_cast<uint32_t>(blk * 32), g);
           tmem_ld_wait();
-          uint32_t wp[16], wd[16];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 ls = lse4[blk * 8 + j4], dm = dsm4[blk * 8 + j4];
@@ -698,21 +737,29 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
             const float p1 = ex2(fmaf(__uint_as_float(r[4 * j4 + 1]), kLog2e, -ls.y));
             const float p2 = ex2(fmaf(__uint_as_float(r[4 * j4 + 2]), kLog2e, -ls.z));
             const float p3 = ex2(fmaf(__uint_as_float(r[4 * j4 + 3]), kLog2e, -ls.w));
-            wp[2 * j4] = pack_bf16(p0, p1);
-            wp[2 * j4 + 1] = pack_bf16(p2, p3);
-            wd[2 * j4] = pack_bf16(p0 * (__uint_as_float(g[4 * j4]) - dm.x), p1 * (__uint_as_float(g[4 * j4 + 1]) - dm.y));
-            wd[2 * j4 + 1] =
+            wp[blk][2 * j4] = pack_bf16(p0, p1);
+            wp[blk][2 * j4 + 1] = pack_bf16(p2, p3);
+            wd[blk][2 * j4] =
+                pack_bf16(p0 * (__uint_as_float(g[4 * j4]) - dm.x), p1 * (__uint_as_float(g[4 * j4 + 1]) - dm.y));
+            wd[blk][2 * j4 + 1] =
                 pack_bf16(p2 * (__uint_as_float(g[4 * j4 + 2]) - dm.z), p3 * (__uint_as_float(g[4 * j4 + 3]) - dm.w));
           }
-          store_row_block(base + kKvPT + sb * kTile, row, blk, wp);
-          store_row_block(base + kKvDST + sb * kTile, row, blk, wd);
         }
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[K_SD_EMPTY + sb]);  // both accumulators are in registers now
+        mbar_wait(&bars[K_PD_EMPTY], (it & 1u) ^ 1u);        // the previous accumulation has read the operand tiles
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          store_row_block(base + kKvPT, row, blk, wp[blk]);
+          store_row_block(base + kKvDST, row, blk, wd[blk]);
+        }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bars[K_PD_FULL + sb]);
-          mbar_arrive(&bars[K_SD_EMPTY + sb]);
+        if (lane == 0) mbar_arrive(&bars[K_PD_FULL]);
+        if (++slot == 3u) {
+          slot = 0;
+          sph ^= 1u;
         }
       }
       mbar_wait(&bars[K_ACC_FULL], tl & 1u);

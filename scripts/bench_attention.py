@@ -24,13 +24,17 @@ def timed(fn, iters=5):
 
 def main():
     dev = torch.device("cuda:0")
+    only = sys.argv[1] if len(sys.argv) > 1 else ""          # substring of a shape name, e.g. "G cc-256"
+    modes = (True,) if "--fused-only" in sys.argv else (False, True)
     for name, (B, Q, Kk, d, dv) in {"G cc-256 (C=384)": (128, 4096, 1024, 48, 192),
                                     "D cc-256 (C=192), fake+real": (256, 4096, 1024, 24, 96),
                                     "G ic-128 (C=128)": (256, 4096, 1024, 16, 64)}.items():
+        if only and not only.startswith("--") and only not in name:
+            continue
         mk = lambda *s: torch.randn(*s, device=dev).bfloat16()
         theta, phi, g, do = mk(B, Q, d), mk(B, Kk, d), mk(B, Kk, dv), mk(B, Q, dv)
         flops_f = 2.0 * B * Q * Kk * (d + dv)
-        for fused in (False, True):
+        for fused in modes:
             ops.FUSED_ATTENTION = fused
             with torch.no_grad():
                 t_f = timed(lambda: ops.AttentionCoreFn.apply(theta, phi, g))
