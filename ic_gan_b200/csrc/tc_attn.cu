@@ -32,7 +32,6 @@
 namespace icgan {
 namespace {
 
-constexpr int kAttnThreads = 192;
 constexpr uint32_t kTile = 16384u;  // 128 rows x 128 bytes (64 bf16), one SWIZZLE_128B operand tile
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -84,12 +83,12 @@ __device__ __forceinline__ void store_row_block(uint32_t chunk_addr, int row, in
 constexpr uint32_t kFwdTheta = 0, kFwdPhi = 2 * kTile, kFwdG = 4 * kTile, kFwdP = 10 * kTile, kFwdBars = 14 * kTile;
 constexpr uint32_t kFwdXch = kFwdBars + 256u;  // 1.5 KB: row maxima / sums exchanged between the two column halves
 constexpr uint32_t kFwdSmem = kFwdXch + 1536u + 1024u;
-constexpr int kFwdThreads = 320;  // TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quadrant)
+constexpr int kAttnThreads = 320;  // all three kernels: TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quadrant)
 static_assert(kFwdSmem <= 227u * 1024u, "forward tile set exceeds shared memory");
 enum FwdBar { F_TH_FULL = 0, F_TH_EMPTY = 2, F_PH_FULL = 4, F_PH_EMPTY = 6, F_G_FULL = 8, F_G_EMPTY = 10, F_S_FULL = 12,
               F_S_EMPTY = 14, F_P_FULL = 16, F_P_EMPTY = 18, F_O_FULL = 20, F_O_EMPTY = 21, F_NBARS = 22 };
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_constant__ CUtensorMap tmPhi,
                 const __grid_constant__ CUtensorMap tmG, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -364,8 +363,8 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < Q_NBARS; ++i) {
-      const bool four = (i == Q_S_EMPTY || i == Q_S_EMPTY + 1 || i == Q_DP_EMPTY || i == Q_DS_FULL || i == Q_DT_EMPTY);
-      mbar_init(&bars[i], four ? 4u : 1u);
+      const bool eight = (i == Q_S_EMPTY || i == Q_S_EMPTY + 1 || i == Q_DP_EMPTY || i == Q_DS_FULL);
+      mbar_init(&bars[i], eight ? 8u : (i == Q_DT_EMPTY ? 4u : 1u));
     }
     fence_barrier_init();
   }
@@ -480,9 +479,11 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
       issue_dq(nc - 1, true);
     }
   } else {
-    const int q = warp & 3;
+    // eight warps: warp w owns TMEM lanes 32 (w mod 4) .. and the 64-column half `hh` of every chunk
+    const int q = warp & 3, hh = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t taddr = lane_base + static_cast<uint32_t>(hh * 64);
     uint32_t tl = 0, si = 0, gi = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
       const int b = tile / p.q_tiles, q0 = (tile % p.q_tiles) * 128;
@@ -504,62 +505,71 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
           }
         }
       }
-      if (p.dsum) p.dsum[grow] = dsum;
-      __nv_bfloat16* dsrow = p.P ? p.P + grow * p.Kk : nullptr;
+      if (p.dsum && hh == 0) p.dsum[grow] = dsum;
+      __nv_bfloat16* dsrow = p.P ? p.P + grow * p.Kk + hh * 64 : nullptr;
       for (int c = 0; c < nc; ++c) {
         const uint32_t sb = si & 1u;
         mbar_wait(&bars[Q_S_FULL + sb], (si >> 1) & 1u);
         mbar_wait(&bars[Q_DP_FULL], gi & 1u);
-        mbar_wait(&bars[Q_DS_EMPTY], (gi & 1u) ^ 1u);
         tc_fence_after();
-#pragma unroll 1
-        for (int blk = 0; blk < 4; ++blk) {
+        uint32_t w[2][16];
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
           uint32_t r[32], g[32];
-          tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(blk * 32), r);
-          tmem_ld32(taddr + 256u + static_cast<uint32_t>(blk * 32), g);
+          tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(b2 * 32), r);
+          tmem_ld32(taddr + 256u + static_cast<uint32_t>(b2 * 32), g);
           tmem_ld_wait();
-          uint32_t w[16];
+          if (b2 == 1) {  // both accumulators are in registers: the MMA warp may overwrite them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&bars[Q_S_EMPTY + sb]);
+              mbar_arrive(&bars[Q_DP_EMPTY]);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float p0 = ex2(fmaf(__uint_as_float(r[2 * j]), kLog2e, -lse));
             const float p1 = ex2(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -lse));
-            w[j] = pack_bf16(p0 * (__uint_as_float(g[2 * j]) - dsum), p1 * (__uint_as_float(g[2 * j + 1]) - dsum));
-          }
-          store_row_block(base + kBwdDS, row, blk, w);
-          if (dsrow) {
-            uint4* dst = reinterpret_cast<uint4*>(dsrow + c * 128 + blk * 32);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+            w[b2][j] = pack_bf16(p0 * (__uint_as_float(g[2 * j]) - dsum), p1 * (__uint_as_float(g[2 * j + 1]) - dsum));
           }
         }
-        tc_fence_before();
+        mbar_wait(&bars[Q_DS_EMPTY], (gi & 1u) ^ 1u);  // dtheta of the previous chunk has read the operand tile
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          store_row_block(base + kBwdDS, row, hh * 2 + b2, w[b2]);
+          if (dsrow) {
+            uint4* dst = reinterpret_cast<uint4*>(dsrow + c * 128 + b2 * 32);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              dst[ch] = make_uint4(w[b2][4 * ch], w[b2][4 * ch + 1], w[b2][4 * ch + 2], w[b2][4 * ch + 3]);
+          }
+        }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bars[Q_S_EMPTY + sb]);
-          mbar_arrive(&bars[Q_DP_EMPTY]);
-          mbar_arrive(&bars[Q_DS_FULL]);
-        }
+        if (lane == 0) mbar_arrive(&bars[Q_DS_FULL]);
         ++si;
         ++gi;
       }
-      mbar_wait(&bars[Q_DT_FULL], tl & 1u);
-      tc_fence_after();
-      __nv_bfloat16* trow = p.dTheta + grow * p.d;
-      for (int c0 = 0; c0 < p.d; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + 384u + static_cast<uint32_t>(c0), r);
-        tmem_ld_wait();
-        uint32_t w[8];
+      if (hh == 0) {
+        mbar_wait(&bars[Q_DT_FULL], tl & 1u);
+        tc_fence_after();
+        __nv_bfloat16* trow = p.dTheta + grow * p.d;
+        for (int c0 = 0; c0 < p.d; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_base + 384u + static_cast<uint32_t>(c0), r);
+          tmem_ld_wait();
+          uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        uint4* dst = reinterpret_cast<uint4*>(trow + c0);
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        if (c0 + 8 < p.d) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          uint4* dst = reinterpret_cast<uint4*>(trow + c0);
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          if (c0 + 8 < p.d) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[Q_DT_EMPTY]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[Q_DT_EMPTY]);
     }
   }
   tc_fence_before();
@@ -599,8 +609,8 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < K_NBARS; ++i) {
-      const bool four = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_ACC_EMPTY);
-      mbar_init(&bars[i], four ? 4u : 1u);
+      const bool eight = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_ACC_EMPTY);
+      mbar_init(&bars[i], eight ? 8u : 1u);
     }
     fence_barrier_init();
   }
@@ -710,9 +720,11 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
       issue_acc(ni - 1, true);
     }
   } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;  // key row of the tile
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // eight warps: warp w owns TMEM lanes (= key rows) 32 (w mod 4) .. and the 32-query block `hh` of every half-tile
+    const int q = warp & 3, hh = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t taddr = lane_base + static_cast<uint32_t>(hh * 32);
     uint32_t tl = 0, it = 0, slot = 0, sph = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
       const int b = tile / k_tiles, k0 = (tile % k_tiles) * 128;
@@ -721,39 +733,34 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
         mbar_wait(&bars[K_ST_FULL + slot], sph);   // lse / dsum of these 64 queries
         mbar_wait(&bars[K_SD_FULL + sb], (it >> 1) & 1u);
         tc_fence_after();
-        const float4* lse4 = reinterpret_cast<const float4*>(smem + kKvStage + slot * kKvStageBytes + 4 * kHalf);
+        const float4* lse4 = reinterpret_cast<const float4*>(smem + kKvStage + slot * kKvStageBytes + 4 * kHalf) + hh * 8;
         const float4* dsm4 = lse4 + 16;
-        uint32_t wp[2][16], wd[2][16];
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
+        uint32_t wp[16], wd[16];
+        {
           uint32_t r[32], g[32];
-          tmem_ld32(taddr + sb * 64u + static_cast<uint32_t>(blk * 32), r);
-          tmem_ld32(taddr + 128u + sb * 64u + static_cast<uint32_t>(blk * 32), g);
+          tmem_ld32(taddr + sb * 64u, r);
+          tmem_ld32(taddr + 128u + sb * 64u, g);
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[K_SD_EMPTY + sb]);  // both accumulators are in registers now
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 ls = lse4[blk * 8 + j4], dm = dsm4[blk * 8 + j4];
+            const float4 ls = lse4[j4], dm = dsm4[j4];
             const float p0 = ex2(fmaf(__uint_as_float(r[4 * j4]), kLog2e, -ls.x));
             const float p1 = ex2(fmaf(__uint_as_float(r[4 * j4 + 1]), kLog2e, -ls.y));
             const float p2 = ex2(fmaf(__uint_as_float(r[4 * j4 + 2]), kLog2e, -ls.z));
             const float p3 = ex2(fmaf(__uint_as_float(r[4 * j4 + 3]), kLog2e, -ls.w));
-            wp[blk][2 * j4] = pack_bf16(p0, p1);
-            wp[blk][2 * j4 + 1] = pack_bf16(p2, p3);
-            wd[blk][2 * j4] =
-                pack_bf16(p0 * (__uint_as_float(g[4 * j4]) - dm.x), p1 * (__uint_as_float(g[4 * j4 + 1]) - dm.y));
-            wd[blk][2 * j4 + 1] =
+            wp[2 * j4] = pack_bf16(p0, p1);
+            wp[2 * j4 + 1] = pack_bf16(p2, p3);
+            wd[2 * j4] = pack_bf16(p0 * (__uint_as_float(g[4 * j4]) - dm.x), p1 * (__uint_as_float(g[4 * j4 + 1]) - dm.y));
+            wd[2 * j4 + 1] =
                 pack_bf16(p2 * (__uint_as_float(g[4 * j4 + 2]) - dm.z), p3 * (__uint_as_float(g[4 * j4 + 3]) - dm.w));
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[K_SD_EMPTY + sb]);  // both accumulators are in registers now
         mbar_wait(&bars[K_PD_EMPTY], (it & 1u) ^ 1u);        // the previous accumulation has read the operand tiles
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          store_row_block(base + kKvPT, row, blk, wp[blk]);
-          store_row_block(base + kKvDST, row, blk, wd[blk]);
-        }
+        store_row_block(base + kKvPT, row, hh, wp);
+        store_row_block(base + kKvDST, row, hh, wd);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[K_PD_FULL]);
@@ -766,28 +773,31 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
       tc_fence_after();
       const int64_t krow = static_cast<int64_t>(b) * p.Kk + k0 + row;
       __nv_bfloat16* grow_ = p.dG + krow * p.dv;
-      for (int c0 = 0; c0 < p.dv; c0 += 16) {
+      const int units = p.dv / 16, u0 = hh == 0 ? 0 : (units + 1) / 2, u1 = hh == 0 ? (units + 1) / 2 : units;
+      for (int u = u0; u < u1; ++u) {
         uint32_t r[16];
-        tmem_ld16(taddr + 256u + static_cast<uint32_t>(c0), r);
+        tmem_ld16(lane_base + 256u + static_cast<uint32_t>(u * 16), r);
         tmem_ld_wait();
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        uint4* dst = reinterpret_cast<uint4*>(grow_ + c0);
+        uint4* dst = reinterpret_cast<uint4*>(grow_ + u * 16);
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
         dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
-      __nv_bfloat16* prow = p.dPhi + krow * p.d;
-      for (int c0 = 0; c0 < p.d; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + 448u + static_cast<uint32_t>(c0), r);
-        tmem_ld_wait();
-        uint32_t w[8];
+      if (hh == 1) {
+        __nv_bfloat16* prow = p.dPhi + krow * p.d;
+        for (int c0 = 0; c0 < p.d; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_base + 448u + static_cast<uint32_t>(c0), r);
+          tmem_ld_wait();
+          uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        uint4* dst = reinterpret_cast<uint4*>(prow + c0);
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        if (c0 + 8 < p.d) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          for (int j = 0; j < 8; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          uint4* dst = reinterpret_cast<uint4*>(prow + c0);
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          if (c0 + 8 < p.d) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -838,7 +848,7 @@ extern "C" int icgan_attn_fwd(const void* theta, const void* phi, const void* g,
   if (first_use_on_this_device(&configured))
     ICGAN_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, p);
+  attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, p);
   ICGAN_LAUNCH_CHECK();
   return 0;
 }
