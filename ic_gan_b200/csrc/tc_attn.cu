@@ -339,6 +339,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// dsum[r] = sum_c a[r][c] * b[r][c]: one warp per row, 16-byte loads, rows of at most 256 bf16 (dv <= 192 here).
+__global__ void __launch_bounds__(256) attn_rowdot_kernel(const __nv_bfloat16* __restrict__ a,
+                                                           const __nv_bfloat16* __restrict__ b, float* __restrict__ out,
+                                                           int64_t rows, int dv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    float acc = 0.f;
+    if (lane * 8 < dv) {
+      const uint4 x = *reinterpret_cast<const uint4*>(a + r * dv + lane * 8);
+      const uint4 y = *reinterpret_cast<const uint4*>(b + r * dv + lane * 8);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[e]));
+        const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[e]));
+        acc = fmaf(fx.x, fy.x, acc);
+        acc = fmaf(fx.y, fy.y, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------- backward, query side
 // shared memory: theta | dO (3 tiles) | phi[2] | g[2] (3 tiles each) | dS (2 tiles) | barriers
 constexpr uint32_t kBwdTheta = 0, kBwdDO = kTile, kBwdPhi = 4 * kTile, kBwdG = 6 * kTile, kBwdDS = 12 * kTile,
@@ -489,23 +516,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
       const int b = tile / p.q_tiles, q0 = (tile % p.q_tiles) * 128;
       const int64_t grow = static_cast<int64_t>(b) * p.Q + q0 + row;
       const float lse = p.lse2[grow];
-      float dsum = 0.f;  // rowsum(dO * o) = rowsum(dP * P)
-      {
-        const uint4* a = reinterpret_cast<const uint4*>(p.dO + grow * p.dv);
-        const uint4* o = reinterpret_cast<const uint4*>(p.O_in + grow * p.dv);
-        for (int j = 0; j < p.dv / 8; ++j) {
-          const uint4 x = a[j], y = o[j];
-          const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[e]));
-            const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[e]));
-            dsum = fmaf(fx.x, fy.x, dsum);
-            dsum = fmaf(fx.y, fy.y, dsum);
-          }
-        }
-      }
-      if (p.dsum && hh == 0) p.dsum[grow] = dsum;
+      const float dsum = p.dsum[grow];  // rowsum(dO * o) = rowsum(dP * P), from attn_rowdot_kernel
       __nv_bfloat16* dsrow = p.P ? p.P + grow * p.Kk + hh * 64 : nullptr;
       for (int c = 0; c < nc; ++c) {
         const uint32_t sb = si & 1u;
@@ -513,20 +524,24 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
         mbar_wait(&bars[Q_DP_FULL], gi & 1u);
         tc_fence_after();
         uint32_t w[2][16];
+        uint32_t g0[32], g1[32];  // dP first: it is single-buffered, and the next chunk's product waits for this read
+        tmem_ld32(taddr + 256u, g0);
+        tmem_ld32(taddr + 256u + 32u, g1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[Q_DP_EMPTY]);
 #pragma unroll
         for (int b2 = 0; b2 < 2; ++b2) {
-          uint32_t r[32], g[32];
+          uint32_t r[32];
           tmem_ld32(taddr + sb * 128u + static_cast<uint32_t>(b2 * 32), r);
-          tmem_ld32(taddr + 256u + static_cast<uint32_t>(b2 * 32), g);
           tmem_ld_wait();
-          if (b2 == 1) {  // both accumulators are in registers: the MMA warp may overwrite them
+          if (b2 == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&bars[Q_S_EMPTY + sb]);
-              mbar_arrive(&bars[Q_DP_EMPTY]);
-            }
+            if (lane == 0) mbar_arrive(&bars[Q_S_EMPTY + sb]);
           }
+          const uint32_t(&g)[32] = b2 == 0 ? g0 : g1;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float p0 = ex2(fmaf(__uint_as_float(r[2 * j]), kLog2e, -lse));
@@ -578,14 +593,17 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------- backward, key side
-// shared memory: phi_t | g_t (3 tiles) | stage[3] = {theta_h 8 KB, dO_h 3 x 8 KB, lse 256 B, dsum 256 B} | P^T | dS^T
+// shared memory: phi_t | g_t (3 tiles) | stage[3] = {theta_h 8 KB, dO_h 3 x 8 KB} | P^T[2] | dS^T[2] |
+//                stage rows[3] = {lse 256 B, dsum 256 B} | barriers
 constexpr uint32_t kHalf = 8192u;  // 64 rows x 128 bytes
-constexpr uint32_t kKvPhi = 0, kKvG = kTile, kKvStage = 4 * kTile, kKvStageBytes = 4 * kHalf + 1024u,
-                   kKvPT = kKvStage + 3 * kKvStageBytes, kKvDST = kKvPT + kTile, kKvBars = kKvDST + kTile;
+constexpr uint32_t kKvPhi = 0, kKvG = kTile, kKvStage = 4 * kTile, kKvStageBytes = 4 * kHalf,
+                   kKvPT = kKvStage + 3 * kKvStageBytes, kKvDST = kKvPT + 2 * kTile, kKvRows = kKvDST + 2 * kTile,
+                   kKvBars = kKvRows + 3 * 512u;
 constexpr uint32_t kKvSmem = kKvBars + 256u + 1024u;
 static_assert(kKvPT % 1024u == 0, "operand tiles must stay 1024-byte aligned");
+static_assert(kKvSmem <= 227u * 1024u, "key-side tile set exceeds shared memory");
 enum KvBar { K_KV_FULL = 0, K_KV_EMPTY = 1, K_ST_FULL = 2, K_ST_EMPTY = 5, K_SD_FULL = 8, K_SD_EMPTY = 10, K_PD_FULL = 12,
-             K_PD_EMPTY = 13, K_ACC_FULL = 14, K_ACC_EMPTY = 15, K_NBARS = 16 };
+             K_PD_EMPTY = 14, K_ACC_FULL = 16, K_ACC_EMPTY = 17, K_NBARS = 18 };
 // TMEM columns: S^T [0,64) [64,128), dP^T [128,192) [192,256), dg [256,448), dphi [448,512)
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -609,7 +627,8 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < K_NBARS; ++i) {
-      const bool eight = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_ACC_EMPTY);
+      const bool eight = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_PD_FULL + 1 ||
+                          i == K_ACC_EMPTY);
       mbar_init(&bars[i], eight ? 8u : 1u);
     }
     fence_barrier_init();
@@ -652,8 +671,8 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
           tma_load_3d(st, &tmThetaH, bar, 0, i * 64, b);
           for (int j = 0; j < p.v_boxes; ++j) tma_load_3d(st + (1 + j) * kHalf, &tmDOH, bar, j * 64, i * 64, b);
           const int64_t qoff = static_cast<int64_t>(b) * p.Q + i * 64;
-          bulk_load_1d(st + 4 * kHalf, p.lse2 + qoff, 256u, bar);
-          bulk_load_1d(st + 4 * kHalf + 256u, p.dsum + qoff, 256u, bar);
+          bulk_load_1d(smem + kKvRows + slot * 512u, p.lse2 + qoff, 256u, bar);
+          bulk_load_1d(smem + kKvRows + slot * 512u + 256u, p.dsum + qoff, 256u, bar);
         }
         __syncwarp();
         if (++slot == 3u) {
@@ -670,21 +689,22 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
       const uint64_t da_phi = umma_desc_kmajor(base + kKvPhi, 128);
       // dg += P^T_j dO_j,  dphi += dS^T_j theta_j  for query half-tile j of this walk
       auto issue_acc = [&](int j, bool last) {
-        mbar_wait(&bars[K_PD_FULL], ia & 1u);
+        const uint32_t pb = ia & 1u;
+        mbar_wait(&bars[K_PD_FULL + pb], (ia >> 1) & 1u);
         if (j == 0) mbar_wait(&bars[K_ACC_EMPTY], (tl & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t st = base + kKvStage + aslot * kKvStageBytes;
           const uint64_t db_do = desc_mn(st + kHalf, kHalf), db_th = desc_mn(st, kHalf);
-          const uint64_t da_p = umma_desc_kmajor(base + kKvPT, 128);
-          const uint64_t da_ds = umma_desc_kmajor(base + kKvDST, 128);
+          const uint64_t da_p = umma_desc_kmajor(base + kKvPT + pb * kTile, 128);
+          const uint64_t da_ds = umma_desc_kmajor(base + kKvDST + pb * kTile, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_bf16(tmem_base + 256u, da_p + 2u * ks, db_do + 128u * ks, p.idesc_o, (j | ks) != 0 ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_bf16(tmem_base + 448u, da_ds + 2u * ks, db_th + 128u * ks, p.idesc_dq, (j | ks) != 0 ? 1u : 0u);
-          umma_commit(&bars[K_PD_EMPTY]);
+          umma_commit(&bars[K_PD_EMPTY + pb]);
           umma_commit(&bars[K_ST_EMPTY + aslot]);
           if (last) umma_commit(&bars[K_ACC_FULL]);
         }
@@ -733,7 +753,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
         mbar_wait(&bars[K_ST_FULL + slot], sph);   // lse / dsum of these 64 queries
         mbar_wait(&bars[K_SD_FULL + sb], (it >> 1) & 1u);
         tc_fence_after();
-        const float4* lse4 = reinterpret_cast<const float4*>(smem + kKvStage + slot * kKvStageBytes + 4 * kHalf) + hh * 8;
+        const float4* lse4 = reinterpret_cast<const float4*>(smem + kKvRows + slot * 512u) + hh * 8;
         const float4* dsm4 = lse4 + 16;
         uint32_t wp[16], wd[16];
         {
@@ -758,12 +778,12 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
                 pack_bf16(p2 * (__uint_as_float(g[4 * j4 + 2]) - dm.z), p3 * (__uint_as_float(g[4 * j4 + 3]) - dm.w));
           }
         }
-        mbar_wait(&bars[K_PD_EMPTY], (it & 1u) ^ 1u);        // the previous accumulation has read the operand tiles
-        store_row_block(base + kKvPT, row, hh, wp);
-        store_row_block(base + kKvDST, row, hh, wd);
+        mbar_wait(&bars[K_PD_EMPTY + sb], ((it >> 1) & 1u) ^ 1u);  // the accumulation two steps back has read these tiles
+        store_row_block(base + kKvPT + sb * kTile, row, hh, wp);
+        store_row_block(base + kKvDST + sb * kTile, row, hh, wd);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[K_PD_FULL]);
+        if (lane == 0) mbar_arrive(&bars[K_PD_FULL + sb]);
         if (++slot == 3u) {
           slot = 0;
           sph ^= 1u;
@@ -856,7 +876,7 @@ extern "C" int icgan_attn_fwd(const void* theta, const void* phi, const void* g,
 extern "C" int icgan_attn_bwd_q(const void* theta, const void* phi, const void* g, const void* o, const void* dout,
                                 const float* lse2, void* dtheta, void* ds, float* dsum, int B, int Q, int Kk, int d,
                                 int dv, void* stream) {
-  ICGAN_REQUIRE(theta && phi && g && o && dout && lse2 && dtheta, "icgan_attn_bwd_q: null pointer");
+  ICGAN_REQUIRE(theta && phi && g && o && dout && lse2 && dtheta && dsum, "icgan_attn_bwd_q: null pointer");
   AttnParams p{};
   if (int rc = fill_params(&p, B, Q, Kk, d, dv, "icgan_attn_bwd_q")) return rc;
   p.O_in = static_cast<const __nv_bfloat16*>(o);
@@ -874,6 +894,9 @@ extern "C" int icgan_attn_bwd_q(const void* theta, const void* phi, const void* 
   if (first_use_on_this_device(&configured))
     ICGAN_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int64_t rows = static_cast<int64_t>(B) * Q;
+  const int dot_blocks = static_cast<int>(rows / 8 < 8 * num_sms() ? (rows + 7) / 8 : 8 * num_sms());
+  attn_rowdot_kernel<<<dot_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p.dO, p.O_in, dsum, rows, dv);
   attn_bwd_q_kernel<<<grid, kAttnThreads, kBwdSmem, static_cast<cudaStream_t>(stream)>>>(tmT, tmP, tmG, tmD, p);
   ICGAN_LAUNCH_CHECK();
   return 0;

@@ -217,7 +217,7 @@ int icgan_attn_fwd(const void* theta, const void* phi, const void* g, void* o, f
                    int dv, void* stream);
 /* Query side of its backward: recomputes the probabilities from lse2, forms dP = dout g^T in tensor memory,
  * ds = probs * (dP - rowsum(dout * o)) and dtheta = ds phi [B,Q,d].  ds (nullable): the bf16 [B,Q,Kk] copy of ds;
- * dsum (nullable): rowsum(dout * o), float32 [B,Q], the input of the key side. */
+ * dsum: rowsum(dout * o), float32 [B,Q], filled by a pre-pass of this call and also the input of the key side. */
 int icgan_attn_bwd_q(const void* theta, const void* phi, const void* g, const void* o, const void* dout,
                      const float* lse2, void* dtheta, void* ds, float* dsum, int B, int Q, int Kk, int d, int dv,
                      void* stream);
