@@ -593,17 +593,20 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmTheta, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------- backward, key side
-// shared memory: phi_t | g_t (3 tiles) | stage[3] = {theta_h 8 KB, dO_h 3 x 8 KB} | P^T[2] | dS^T[2] |
-//                stage rows[3] = {lse 256 B, dsum 256 B} | barriers
+// shared memory: phi_t | g_t (3 tiles) | stage[4] = {theta_h 8 KB, dO_h 3 x 8 KB} | P^T | dS^T |
+//                stage rows[4] = {lse 256 B, dsum 256 B} | barriers
 constexpr uint32_t kHalf = 8192u;  // 64 rows x 128 bytes
+constexpr uint32_t kKvSlots = 4;   // the walk is latency-bound on these loads: each extra stage in flight pays directly
 constexpr uint32_t kKvPhi = 0, kKvG = kTile, kKvStage = 4 * kTile, kKvStageBytes = 4 * kHalf,
-                   kKvPT = kKvStage + 3 * kKvStageBytes, kKvDST = kKvPT + 2 * kTile, kKvRows = kKvDST + 2 * kTile,
-                   kKvBars = kKvRows + 3 * 512u;
-constexpr uint32_t kKvSmem = kKvBars + 256u + 1024u;
+                   kKvPT = kKvStage + kKvSlots * kKvStageBytes, kKvDST = kKvPT + kTile, kKvRows = kKvDST + kTile,
+                   kKvBars = kKvRows + kKvSlots * 512u;
+// four 32 KB stages leave 864 bytes for re-aligning the dynamic window to 1024; it starts right after the 1 KB the
+// system reserves, i.e. aligned, and the kernel traps if a toolchain ever places it otherwise
+constexpr uint32_t kKvSmem = 227u * 1024u, kKvAlignSlack = kKvSmem - (kKvBars + 160u);
 static_assert(kKvPT % 1024u == 0, "operand tiles must stay 1024-byte aligned");
-static_assert(kKvSmem <= 227u * 1024u, "key-side tile set exceeds shared memory");
-enum KvBar { K_KV_FULL = 0, K_KV_EMPTY = 1, K_ST_FULL = 2, K_ST_EMPTY = 5, K_SD_FULL = 8, K_SD_EMPTY = 10, K_PD_FULL = 12,
-             K_PD_EMPTY = 14, K_ACC_FULL = 16, K_ACC_EMPTY = 17, K_NBARS = 18 };
+static_assert(kKvBars + 160u <= kKvSmem, "key-side tile set exceeds shared memory");
+enum KvBar { K_KV_FULL = 0, K_KV_EMPTY = 1, K_ST_FULL = 2, K_ST_EMPTY = 6, K_SD_FULL = 10, K_SD_EMPTY = 12, K_PD_FULL = 14,
+             K_PD_EMPTY = 15, K_ACC_FULL = 16, K_ACC_EMPTY = 17, K_NBARS = 18 };
 // TMEM columns: S^T [0,64) [64,128), dP^T [128,192) [192,256), dg [256,448), dphi [448,512)
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -621,14 +624,14 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
+  if (base - raw > kKvAlignSlack) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKvBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + K_NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < K_NBARS; ++i) {
-      const bool eight = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_PD_FULL + 1 ||
-                          i == K_ACC_EMPTY);
+      const bool eight = (i == K_SD_EMPTY || i == K_SD_EMPTY + 1 || i == K_PD_FULL || i == K_ACC_EMPTY);
       mbar_init(&bars[i], eight ? 8u : 1u);
     }
     fence_barrier_init();
@@ -675,7 +678,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
           bulk_load_1d(smem + kKvRows + slot * 512u + 256u, p.dsum + qoff, 256u, bar);
         }
         __syncwarp();
-        if (++slot == 3u) {
+        if (++slot == kKvSlots) {
           slot = 0;
           sph ^= 1u;
         }
@@ -689,28 +692,27 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
       const uint64_t da_phi = umma_desc_kmajor(base + kKvPhi, 128);
       // dg += P^T_j dO_j,  dphi += dS^T_j theta_j  for query half-tile j of this walk
       auto issue_acc = [&](int j, bool last) {
-        const uint32_t pb = ia & 1u;
-        mbar_wait(&bars[K_PD_FULL + pb], (ia >> 1) & 1u);
+        mbar_wait(&bars[K_PD_FULL], ia & 1u);
         if (j == 0) mbar_wait(&bars[K_ACC_EMPTY], (tl & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t st = base + kKvStage + aslot * kKvStageBytes;
           const uint64_t db_do = desc_mn(st + kHalf, kHalf), db_th = desc_mn(st, kHalf);
-          const uint64_t da_p = umma_desc_kmajor(base + kKvPT + pb * kTile, 128);
-          const uint64_t da_ds = umma_desc_kmajor(base + kKvDST + pb * kTile, 128);
+          const uint64_t da_p = umma_desc_kmajor(base + kKvPT, 128);
+          const uint64_t da_ds = umma_desc_kmajor(base + kKvDST, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_bf16(tmem_base + 256u, da_p + 2u * ks, db_do + 128u * ks, p.idesc_o, (j | ks) != 0 ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_bf16(tmem_base + 448u, da_ds + 2u * ks, db_th + 128u * ks, p.idesc_dq, (j | ks) != 0 ? 1u : 0u);
-          umma_commit(&bars[K_PD_EMPTY + pb]);
+          umma_commit(&bars[K_PD_EMPTY]);
           umma_commit(&bars[K_ST_EMPTY + aslot]);
           if (last) umma_commit(&bars[K_ACC_FULL]);
         }
         __syncwarp();
         ++ia;
-        if (++aslot == 3u) aslot = 0;
+        if (++aslot == kKvSlots) aslot = 0;
       };
       for (int i = 0; i < ni; ++i, ++it) {
         const uint32_t sb = it & 1u;
@@ -731,7 +733,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
           if (i == ni - 1) umma_commit(&bars[K_KV_EMPTY]);  // phi_t and g_t have no reader after these products
         }
         __syncwarp();
-        if (++slot == 3u) {
+        if (++slot == kKvSlots) {
           slot = 0;
           sph ^= 1u;
         }
@@ -778,13 +780,13 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmThetaH, const __grid_co
                 pack_bf16(p2 * (__uint_as_float(g[4 * j4 + 2]) - dm.z), p3 * (__uint_as_float(g[4 * j4 + 3]) - dm.w));
           }
         }
-        mbar_wait(&bars[K_PD_EMPTY + sb], ((it >> 1) & 1u) ^ 1u);  // the accumulation two steps back has read these tiles
-        store_row_block(base + kKvPT + sb * kTile, row, hh, wp);
-        store_row_block(base + kKvDST + sb * kTile, row, hh, wd);
+        mbar_wait(&bars[K_PD_EMPTY], (it & 1u) ^ 1u);        // the previous accumulation has read the operand tiles
+        store_row_block(base + kKvPT, row, hh, wp);
+        store_row_block(base + kKvDST, row, hh, wd);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[K_PD_FULL + sb]);
-        if (++slot == 3u) {
+        if (lane == 0) mbar_arrive(&bars[K_PD_FULL]);
+        if (++slot == kKvSlots) {
           slot = 0;
           sph ^= 1u;
         }
