@@ -721,7 +721,7 @@ def main():
     ap.add_argument("--sg-cpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--torch-profile", default="", help="sg256: write a per-kernel device-time table (torch.profiler, 16 eager "
                                                        "iterations) to this path and exit; shares only, never a bench value")
-    ap.add_argument("--no-graphs", action="store_true", help="sg256: issue every launch from Python instead of replaying "
+    ap.add_argument("--no-graphs", action="store_true", help="issue every launch from Python instead of replaying "
                                                              "one CUDA graph per loss phase")
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: short warm-up allowed, no e2e/cpu legs "
                                                        "(a number printed by such a run is never a bench value)")
@@ -806,14 +806,24 @@ def main():
         cursor[0] += 1
         return (z_pool[i], yg_pool[i], fg_pool[i]) if cc else (z_pool[i], fg_pool[i])
 
+    # micro-steps replayed from CUDA graphs (ic_gan_b200/biggan/graphs.py) unless --no-graphs / profiling: ~4 400 launches
+    # per step, ~9 % of the eager step is the device waiting for Python between the small ones
+    graphed = not (args.no_graphs or args.ncu or args.torch_profile)
     train_dev = train_fns.GAN_training_function(G, D, GD, ema, state, config, sample_dev, embedded_optimizers=False,
-                                                device=dev, batch_size=m, grad_sync=sync, lazy_losses=True)
+                                                device=dev, batch_size=m, grad_sync=sync, lazy_losses=True,
+                                                graphs=graphed)
+    train_eager = train_dev if not graphed else train_fns.GAN_training_function(
+        G, D, GD, ema, state, config, sample_dev, embedded_optimizers=False, device=dev, batch_size=m, grad_sync=sync,
+        lazy_losses=True)
 
-    def step_dev():
+    def step_dev(fn=None):
         sync.broadcast_buffers()
-        out = train_dev(x_dev, y_dev, f_dev)
+        out = (fn or train_dev)(x_dev, y_dev, f_dev)
         state["itr"] += 1
         return out
+
+    def replayed():
+        return train_dev.graphs.replayed_launches if graphed else 0
 
     def barrier():
         if world > 1:
@@ -841,18 +851,34 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.PROFILE = [] if rank == 0 else None
-    launches0 = _lib.LAUNCHES
+    ops.PROFILE = [] if (rank == 0 and not graphed) else None
+    launches0 = _lib.LAUNCHES + replayed()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step_dev()
     e1.record()
     barrier()
-    launches = _lib.LAUNCHES - launches0
+    launches = _lib.LAUNCHES + replayed() - launches0
     prof = ops.PROFILE
     ops.PROFILE = None
     ms = e0.elapsed_time(e1) / args.steps
+    prof_steps, prof_ms = args.steps, ms
+    if graphed and rank == 0:
+        # per-kernel CUDA events cannot be recorded inside a graph: the tensor-core launches are timed in an eager,
+        # instrumented pass over the same step right after the timed region (same kernels, shapes and data)
+        prof_steps = min(args.steps, 3)
+        ops.PROFILE = []
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(prof_steps):
+            step_dev(train_eager)
+        p1.record()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        prof_ms = p0.elapsed_time(p1) / prof_steps
+    if world > 1:
+        barrier()
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -881,7 +907,7 @@ def main():
 
         train_host = train_fns.GAN_training_function(G, D, GD, ema, state, config, sample_host,
                                                      embedded_optimizers=False, device=dev, batch_size=m,
-                                                     grad_sync=sync)
+                                                     grad_sync=sync, graphs=train_dev.graphs if graphed else False)
 
         def step_host():
             sync.broadcast_buffers()
@@ -934,7 +960,7 @@ def main():
             print(f"# {name:16s} {str(shape):34s} {v[2]:5d} {v[1]*1e3:9.2f} {100*v[1]/tot:5.1f}% {v[0]/v[1]*1e-12:8.1f}",
                   file=sys.stderr)
     kinfo = {k: {"launches": v[2], "avg_ms": v[1] / v[2] * 1e3, "tflops": v[0] / v[1] * 1e-12,
-                 "share_of_step": v[1] / (ms * 1e-3 * args.steps)} for k, v in per_kernel.items()}
+                 "share_of_step": v[1] / (prof_ms * 1e-3 * prof_steps)} for k, v in per_kernel.items()}
     dom = max(per_kernel, key=lambda k: per_kernel[k][1]) if per_kernel else None
     roofline = None
     if dom:
@@ -952,7 +978,9 @@ def main():
         roofline = {"kernel": label, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sustained"], "traffic": traffic, "traffic_launch": traffic_launch,
                     "peak_source": pk["source"] + ", sustained",
-                    "flops_per_launch": per_kernel[dom][0] / per_kernel[dom][2], "kernels": kinfo}
+                    "flops_per_launch": per_kernel[dom][0] / per_kernel[dom][2], "kernels": kinfo,
+                    "timed_in": (f"eager instrumented pass of {prof_steps} steps ({prof_ms:.1f} ms each) right after the "
+                                 "graph-replayed timed region" if graphed else "the timed region")}
     f_step = 4 * w["G_f"] + 8 * w["D_f"]  # GF per image, reference step model
     step_tf = f_step * 1e9 * value / world * 1e-12
     line = {"metric": f"{METRIC} {R}x{R}", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -961,6 +989,7 @@ def main():
             "config": {"workload": w["name"], "per_gpu_batch": Bg, "micro_batch": m, "accumulations": acc,
                        "global_batch": Bg * world, "parallelism": f"dp{world}", "l2": "inputs larger than L2",
                        "optimizer": "icgan_adam_ema_step: Adam + EMA fused, one launch per network", "step_gflop_per_image": f_step,
+                       "cuda_graphs": graphed,
                        "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
             "roofline": roofline,
             "step_roofline": {"achieved_tflops_per_gpu": step_tf, "frac_of_sustained_peak": step_tf / pk["tf_sustained"]},

@@ -64,10 +64,33 @@ class ema(object):
 
 
 def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditionings, embedded_optimizers=True,
-                          device="cuda", batch_size=0, grad_sync=None, lazy_losses=False):
-    """`grad_sync` / `lazy_losses` are extensions (defaults = reference behaviour): see the module docstring; with
-    lazy_losses=True train() returns 0-d device tensors instead of the reference's Python floats (train_fns.py:183-187),
-    leaving the host free to queue the next step."""
+                          device="cuda", batch_size=0, grad_sync=None, lazy_losses=False, graphs=False):
+    """`grad_sync` / `lazy_losses` / `graphs` are extensions (defaults = reference behaviour): see the module docstring;
+    with lazy_losses=True train() returns 0-d device tensors instead of the reference's Python floats
+    (train_fns.py:183-187), leaving the host free to queue the next step; with graphs=True every micro-step (forward +
+    loss + backward of one accumulation) is captured into a CUDA graph on first use and replayed afterwards
+    (biggan/graphs.py; pass a GraphedMicroSteps to share
+    captured graphs between training functions over the same networks); the object is exposed as train.graphs."""
+    graphed = None
+    if graphs:
+        from .graphs import GraphedMicroSteps
+        graphed = graphs if isinstance(graphs, GraphedMicroSteps) else GraphedMicroSteps({"G": G, "D": D})
+    n_d_acc, n_g_acc = float(config["num_D_accumulations"]), float(config["num_G_accumulations"])
+
+    def _d_micro(z, gy, fg, x, dy, f):
+        D_fake, D_real = GD(z, gy, fg, x, dy, f, train_G=False, split_D=config["split_D"],
+                            policy=config.get("DiffAugment", False), DA=config.get("DA", False))
+        D_loss_real, D_loss_fake = loss_hinge_dis(D_fake, D_real)
+        ((D_loss_real + D_loss_fake) / n_d_acc).backward()
+        return D_loss_real.detach(), D_loss_fake.detach()
+
+    def _g_micro(z, gy, fg):
+        D_fake = GD(z, gy, fg, train_G=True, split_D=config["split_D"], policy=config.get("DiffAugment", False),
+                    DA=config.get("DA", False))
+        G_loss = loss_hinge_gen(D_fake) / n_g_acc
+        G_loss.backward()
+        return (G_loss.detach(),)
+
     def _opt(net, name):
         return net.optim if embedded_optimizers else getattr(GD, name)
 
@@ -110,12 +133,9 @@ def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditioning
             _zero(opt_D)
             for _ in range(config["num_D_accumulations"]):
                 z_, labels_g, f_g = _draw(y is not None, features is not None, batch_size)
-                D_fake, D_real = GD(z_, labels_g, f_g, xs[counter], ys[counter] if ys is not None else None,
-                                    fs[counter] if fs is not None else None, train_G=False,
-                                    split_D=config["split_D"], policy=config.get("DiffAugment", False),
-                                    DA=config.get("DA", False))
-                D_loss_real, D_loss_fake = loss_hinge_dis(D_fake, D_real)
-                ((D_loss_real + D_loss_fake) / float(config["num_D_accumulations"])).backward()
+                args = dict(z=z_, gy=labels_g, fg=f_g, x=xs[counter], dy=ys[counter] if ys is not None else None,
+                            f=fs[counter] if fs is not None else None)
+                D_loss_real, D_loss_fake = graphed.run("D", _d_micro, **args) if graphed else _d_micro(**args)
                 counter += 1
             if config.get("D_ortho", 0.0) > 0.0:
                 raise NotImplementedError("ortho regularisation is off in every IC-GAN config")
@@ -128,10 +148,8 @@ def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditioning
         _zero(opt_G)
         for _ in range(config["num_G_accumulations"]):
             z_, labels_g, f_g = _draw(y is not None, features is not None, None)
-            D_fake = GD(z_, labels_g, f_g, train_G=True, split_D=config["split_D"],
-                        policy=config.get("DiffAugment", False), DA=config.get("DA", False))
-            G_loss = loss_hinge_gen(D_fake) / float(config["num_G_accumulations"])
-            G_loss.backward()
+            args = dict(z=z_, gy=labels_g, fg=f_g)
+            (G_loss,) = graphed.run("G", _g_micro, **args) if graphed else _g_micro(**args)
         if config.get("G_ortho", 0.0) > 0.0:
             raise NotImplementedError("ortho regularisation is off in every IC-GAN config")
         if grad_sync is not None:
@@ -141,10 +159,12 @@ def GAN_training_function(G, D, GD, ema, state_dict, config, sample_conditioning
         opt_G.step()
         if config["ema"]:
             ema.update(state_dict["itr"])
+        # (with graphs the three tensors are the graphs' static outputs: read or clone them before the next step)
         out = {"G_loss": G_loss.detach(), "D_loss_real": D_loss_real.detach(), "D_loss_fake": D_loss_fake.detach()}
         if lazy_losses:
             return out
         vals = torch.stack([out["G_loss"].float(), out["D_loss_real"].float(), out["D_loss_fake"].float()]).tolist()
         return {"G_loss": vals[0], "D_loss_real": vals[1], "D_loss_fake": vals[2]}  # one device->host read (12 bytes)
 
+    train.graphs = graphed
     return train

@@ -452,14 +452,20 @@ def _up_slices():
 _UP_SLICES = _up_slices()
 
 
+_MERGE_CACHE = {}  # (kind, device) -> constant matrix, built once (and never inside a CUDA-graph capture)
+
+
 def up_merge_matrix(device):
     """M[t, kh*3+kw] = 1 where 3x3 tap (kh, kw) is merged into slice t (float32 [16, 9])."""
+    if ("up", device) in _MERGE_CACHE:
+        return _MERGE_CACHE[("up", device)]
     M = torch.zeros(16, 9)
     for t, (_, _, _, _, rows, cols) in enumerate(_UP_SLICES):
         for kh in rows:
             for kw in cols:
                 M[t, kh * 3 + kw] = 1.0
-    return M.to(device)
+    _MERGE_CACHE[("up", device)] = M.to(device)
+    return _MERGE_CACHE[("up", device)]
 
 
 class UpConvFn(torch.autograd.Function):
@@ -534,6 +540,8 @@ POOLED_DOWN = bool(int(__import__("os").environ.get("ICGAN_POOLED_DOWN", "1")))
 
 def down_merge_matrix(device):
     """M[t = r*4+s, kh*3+kw] = 1/4 where tap (kh, kw) of the 3x3 kernel contributes to tap (r, s) of the 4x4 one."""
+    if ("down", device) in _MERGE_CACHE:
+        return _MERGE_CACHE[("down", device)]
     M = torch.zeros(16, 9)
     for r in range(4):
         for s_ in range(4):
@@ -541,7 +549,8 @@ def down_merge_matrix(device):
                 for kw in range(3):
                     if 0 <= r - kh <= 1 and 0 <= s_ - kw <= 1:
                         M[r * 4 + s_, kh * 3 + kw] = 0.25
-    return M.to(device)
+    _MERGE_CACHE[("down", device)] = M.to(device)
+    return _MERGE_CACHE[("down", device)]
 
 
 _DOWN_ADJ = {0: ((0, 1), (-1, 3)), 1: ((1, 0), (0, 2))}  # output parity -> ((source offset in the pooled grid, 4x4 tap row), ...)
@@ -699,8 +708,11 @@ class BNActFn(torch.autograd.Function):
             prev = hint.get("mean") if hint is not None else None  # last step's batch mean centres the one-pass moments
             call("icgan_bn_train_stats", ptr(x), B * H * W, Cc, dt(x), ptr(ws), ptr(prev), ptr(running_mean),
                  ptr(running_var), ptr(mean), ptr(invstd), float(eps), float(momentum), stream_ptr())
-            if hint is not None:
-                hint["mean"] = mean
+            if hint is not None:  # a persistent buffer: a captured CUDA graph keeps reading (and refreshing) this address
+                if prev is None or prev.shape != mean.shape:
+                    hint["mean"] = mean.clone()
+                else:
+                    prev.copy_(mean)
         else:
             mean = running_mean.float()
             invstd = torch.rsqrt(running_var.float() + eps)

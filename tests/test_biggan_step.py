@@ -79,8 +79,11 @@ def test_oracle_train_step_matches_reference_golden():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("graphs", [False, True], ids=["eager", "cuda_graphs"])
 @pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
-def test_gpu_training_function_matches_reference_golden(cuda_device, cdt):
+def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs):
+    """graphs=True: every micro-step is captured into a CUDA graph on first use (biggan/graphs.py) -- the very first call
+    of the test captures, so the stash / restore around the warm-up executions is held to the same golden."""
     from ic_gan_b200.biggan import G_D, Discriminator, Generator, train_fns
     meta, fx = _load()
     cfg, hp = O.BigGANConfig(**meta["config"]), meta["hp"]
@@ -105,13 +108,15 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt):
                   split_D=False, DiffAugment=False, DA=False, D_ortho=0.0, G_ortho=0.0, ema=True)
     state = {"itr": 0}
     train = train_fns.GAN_training_function(G, D, GD, ema, state, config, lambda: next(it), embedded_optimizers=True,
-                                            device=dev, batch_size=hp["batch_size"])
+                                            device=dev, batch_size=hp["batch_size"], graphs=graphs)
     losses = []
     for (x, y, f) in calls:
         out = train(x.to(dev), y.to(dev), f.to(dev))
         assert all(isinstance(v, float) for v in out.values())  # the reference returns Python floats (train_fns.py:183-187)
         losses.append([out["G_loss"], out["D_loss_real"], out["D_loss_fake"]])
         state["itr"] += 1
+    if graphs:
+        assert len(train.graphs.graphs) == 2 and train.graphs.replayed_launches > 0  # one D graph, one G graph, replayed
     ref_losses = fx["losses"].numpy()
     print(f"step {cdt}: losses {losses} vs reference {ref_losses.tolist()}")
     if cdt == torch.float32:
