@@ -119,22 +119,48 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs
         assert len(train.graphs.graphs) == 2 and train.graphs.replayed_launches > 0  # one D graph, one G graph, replayed
     ref_losses = fx["losses"].numpy()
     print(f"step {cdt}: losses {losses} vs reference {ref_losses.tolist()}")
+    def update_error(tag, net_sd, sd0, lr):
+        """worst per-tensor rel-L2 of (w_after - w_before) against the reference's update; tensors whose reference
+        update is rounding noise (e.g. conv biases feeding a batch norm) are skipped."""
+        worst, worst_k = 0.0, ""
+        for k, w0 in sd0.items():
+            if f"{tag}/{k}" not in fx or not O.is_param(k, net_sd[k]):
+                continue
+            w0s = sample_of(w0)
+            upd_ref = fx[f"{tag}/{k}"] - w0s
+            if upd_ref.norm() < 0.05 * lr * upd_ref.numel() ** 0.5:
+                continue
+            e = float((sample_of(net_sd[k].detach().float().cpu()) - w0s - upd_ref).norm() / upd_ref.norm())
+            if e > worst:
+                worst, worst_k = e, f"{tag}.{k}"
+        return worst, worst_k
+
     if cdt == torch.float32:
         assert np.allclose(np.array(losses), ref_losses, atol=2e-3 * max(1.0, np.abs(ref_losses).max()))
-        # 0.5 x lr: the GPU's float32 summation orders (atomics in wgrad / embedding backward) differ run to run and three
-        # Adam steps amplify that (a slightly different first step moves every later gradient); measured worst
-        # well-conditioned element over four runs: 0.12, 0.12, 0.28, 0.09 x lr (the CPU oracle: 0.03 x lr).  A wrong
-        # schedule (EMA start, accumulation, toggling, optimiser order) moves weights by whole multiples of lr.
-        wg = _check("G", G.state_dict(), fx, hp["G_lr"], 0.5, hp=hp)
-        wd = _check("D", D.state_dict(), fx, hp["D_lr"], 0.5, hp=hp)
-        we = _check("G_ema", G_ema.state_dict(), fx, hp["G_lr"], 0.5, hp=hp)
+        # The GPU's float32 summation orders (atomics in wgrad / embedding backward) differ run to run, and this fixture
+        # (lr 1e-3 / 2e-3 against adam_eps 1e-4) amplifies that: D's first Adam step turns 4e-6 relative gradient noise
+        # into 1.4e-5 in the weights, G's gradient through that D differs by 2e-4, and from there the trajectory lands in
+        # one of a few discrete branches.  Sixteen runs, eager and CUDA-graph mode alike (profiles/r02_step_parity_spread.txt):
+        # worst well-conditioned element 0.003 .. 0.28 x lr in eleven of them, 1.1 .. 2.0 x lr in five; worst per-tensor
+        # update rel-L2 9e-4 .. 9.1e-2 in all of them.  So: every tensor's UPDATE within 0.25 rel-L2 of the reference's
+        # (a wrong schedule -- EMA start, accumulation, toggling, optimiser order -- changes updates by O(1)), and
+        # every element within the 3 x lr that three Adam steps can move it.
+        wg = _check("G", G.state_dict(), fx, hp["G_lr"], 3.0, buf_tol=5e-3, hp=hp)
+        wd = _check("D", D.state_dict(), fx, hp["D_lr"], 3.0, buf_tol=5e-3, hp=hp)
+        we = _check("G_ema", G_ema.state_dict(), fx, hp["G_lr"], 3.0, buf_tol=5e-3, hp=hp)
         print(f"step fp32: worst |w - w_ref| / lr: G {wg:.3e}, D {wd:.3e}, G_ema {we:.3e}")
+        ug = update_error("G", G.state_dict(), g_sd0, hp["G_lr"])
+        ud = update_error("D", D.state_dict(), d_sd0, hp["D_lr"])
+        ue = update_error("G_ema", G_ema.state_dict(), g_sd0, hp["G_lr"])
+        print(f"step fp32: worst per-tensor update rel-L2: G {ug[0]:.3e} ({ug[1]}), D {ud[0]:.3e} ({ud[1]}), "
+              f"G_ema {ue[0]:.3e} ({ue[1]})")
+        assert max(ug[0], ud[0], ue[0]) <= 0.25, (ug, ud, ue)
         for tag, net in (("G", G), ("D", D)):
             for k, p in net.named_parameters():
                 for mom in ("exp_avg", "exp_avg_sq"):
                     ref = fx[f"{tag}_{mom}/{k}"]
                     got = sample_of(net.optim.state[p][mom].float().cpu())
-                    assert (got - ref).norm() <= 2e-2 * ref.norm() + 1e-5 * ref.numel() ** 0.5, f"{tag} {mom} {k}"
+                    assert (got - ref).norm() <= 0.25 * ref.norm() + 1e-5 * ref.numel() ** 0.5, f"{tag} {mom} {k}"
     else:
         # bf16 tensor-core mode: per-element agreement of an Adam update is not a meaningful bar (a gradient element whose
         # bf16 noise exceeds adam_eps moves by a different fraction of lr); hold the losses and the per-tensor UPDATE
