@@ -12,8 +12,9 @@ EMA stay outside (train_fns.py).
 Exactness: capture needs warm-up executions, which would otherwise leave their marks (gradients accumulated, batch-norm
 running statistics and the power-iteration vector advanced).  ``run`` therefore stashes every gradient and buffer of both
 networks before warming up, restores them after capture and only then replays, so the capturing call has exactly the
-effect of one eager micro-step.  The operand copies of the weights (ops.SNState.prepare) are rebuilt inside every
-replay: the graph cannot ask Python whether an optimiser step happened in between."""
+effect of one eager micro-step.  The operand copies of the weights (ops.SNState.prepare: bf16 re-layouts, merged up- /
+down-sampling kernels) are persistent buffers rewritten in place, and they are NOT part of the graphs: ``run`` rebuilds
+them eagerly before a replay iff an optimiser step happened since (a replay runs no Python that could notice)."""
 from __future__ import annotations
 
 from typing import Callable, Dict, Optional
@@ -52,7 +53,7 @@ class GraphedMicroSteps:
             for _ in range(self.warmup):
                 fn(**st)
         torch.cuda.current_stream().wait_stream(side)
-        ops.invalidate_operands()  # capture the weight re-layout too: replays follow optimiser steps Python cannot see
+        self._refresh_operands()  # nothing to rebuild right after the warm-up: no re-layout kernel lands in the graph
         before = _lib.LAUNCHES
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -62,12 +63,19 @@ class GraphedMicroSteps:
         self.graphs[key], self.static[key], self.outputs[key] = g, st, out
         self.launches[key] = _lib.LAUNCHES - before
 
+    def _refresh_operands(self):
+        before = _lib.LAUNCHES
+        for net in self.nets.values():
+            net.prepare_operands()
+        return _lib.LAUNCHES - before
+
     def run(self, name: str, fn: Callable, **inputs):
         """fn(**inputs) -> tuple of tensors; later calls with inputs of the same shapes replay the captured graph and
         return the same (static) output tensors."""
         key = (name,) + tuple((k, tuple(v.shape), v.dtype) if v is not None else (k, None) for k, v in inputs.items())
         if key not in self.graphs:
             self._capture(key, fn, inputs)
+        self._refresh_operands()
         st = self.static[key]
         for k, v in inputs.items():
             if v is not None:

@@ -94,7 +94,7 @@ class SNConv2d(nn.Conv2d, SN):
     def upconv_nhwc(self, x):
         """conv3x3(nearest_up2(x)) in sub-pixel form (ops.UpConvFn): x is the LOW-resolution tensor."""
         st = self._sn_ready()
-        if getattr(st, "up_version", None) != (self.weight._version, ops._WEIGHT_EPOCH[0]):
+        if getattr(st, "up_version", None) != ops.weight_stamp(self.weight):
             with torch.no_grad():
                 st.build_up_operands()  # first use, or the weights changed since the slices were merged
         return ops.UpConvFn.apply(x, self.weight, self.bias, st)
@@ -102,7 +102,7 @@ class SNConv2d(nn.Conv2d, SN):
     def downconv_nhwc(self, x, residual=None, mask_input=False):
         """avgpool2(conv3x3(x)) + residual as one stride-2 4x4 convolution (ops.DownConvFn)."""
         st = self._sn_ready()
-        if getattr(st, "down_version", None) != (self.weight._version, ops._WEIGHT_EPOCH[0]):
+        if getattr(st, "down_version", None) != ops.weight_stamp(self.weight):
             with torch.no_grad():
                 st.build_down_operands()
         return ops.DownConvFn.apply(x, self.weight, self.bias, residual, st, mask_input)

@@ -95,6 +95,14 @@ class _SNNetwork(nn.Module):
         with torch.no_grad():
             ops.refresh_sn(self._sn_states, self.training, self.SN_eps, self.compute_dtype, self._sn_cache)
 
+    def prepare_operands(self):
+        """Rebuild the operand copies of every layer whose master weight changed since they were built -- what each
+        forward does through refresh_sn; the graph-replay path (biggan/graphs.py) calls it because a replay runs no Python."""
+        if getattr(self, "_sn_states", None):
+            with torch.no_grad():
+                for s in self._sn_states:
+                    s.prepare()
+
     def _apply(self, fn, *args, **kwargs):  # .to()/.cuda() move parameters: drop cached device tables
         out = super()._apply(fn, *args, **kwargs)
         self._sn_states = None

@@ -43,13 +43,27 @@ _SHAPE = [None]  # set by the conv wrappers so bench.py can attribute time to la
 
 # ===================================================================================== spectral-norm state
 # Operand copies of a conv weight are rebuilt when the master weight may have changed.  Signals: the tensor version
-# counter (load_state_dict, in-place ops), a process-wide counter bumped after EVERY optimizer step (fused optimizers
-# do not bump tensor versions), eval mode (always rebuild: EMA copies are written through .data), or invalidate_operands().
+# counter (load_state_dict, in-place ops), a per-parameter counter bumped by a post-step hook on every optimiser that
+# owns it (fused optimisers do not bump tensor versions), eval mode (always rebuild: EMA copies are written through
+# .data), or invalidate_operands() with no argument (everything).
 _WEIGHT_EPOCH = [0]
+_PARAM_EPOCH = {}  # id(parameter) -> number of optimiser steps that have touched it
 
 
-def invalidate_operands(*_args, **_kwargs) -> None:
-    _WEIGHT_EPOCH[0] += 1
+def invalidate_operands(*args, **_kwargs) -> None:
+    """Optimiser post-step hook (args[0] = the optimiser: only ITS parameters are stale -- G's operands survive D's step)
+    or, called with no optimiser, a global invalidation."""
+    opt = args[0] if args and hasattr(args[0], "param_groups") else None
+    if opt is None:
+        _WEIGHT_EPOCH[0] += 1
+        return
+    for group in opt.param_groups:
+        for p in group["params"]:
+            _PARAM_EPOCH[id(p)] = _PARAM_EPOCH.get(id(p), 0) + 1
+
+
+def weight_stamp(w) -> tuple:
+    return (w._version, _WEIGHT_EPOCH[0], _PARAM_EPOCH.get(id(w), 0))
 
 
 from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
@@ -153,12 +167,30 @@ class SNState:
             return out
         return wk
 
+    def _keep(self, name: str, value: Tensor) -> Tensor:
+        """Operand copies are PERSISTENT buffers rewritten in place: a captured CUDA graph (biggan/graphs.py) bakes their
+        addresses, and the eager path stops allocating per rebuild."""
+        cur = getattr(self, name, None)
+        if cur is not None and cur.shape == value.shape and cur.dtype == value.dtype and cur.device == value.device:
+            cur.copy_(value)
+            return cur
+        value = value.contiguous()
+        setattr(self, name, value)
+        return value
+
+    def _slot(self, name: str, shape, dtype, device) -> Tensor:
+        cur = getattr(self, name, None)
+        if cur is None or tuple(cur.shape) != tuple(shape) or cur.dtype != dtype or cur.device != device:
+            cur = torch.empty(*shape, device=device, dtype=dtype)
+            setattr(self, name, cur)
+        return cur
+
     def prepare(self):
         """(Re)build the operand copies iff the master weight changed since the last build."""
         w = self.module.weight
         if self.kind != "conv":
             return
-        stamp = (w._version, _WEIGHT_EPOCH[0])
+        stamp = weight_stamp(w)
         if self.version == stamp and self.module.training:
             return
         self.version = stamp
@@ -171,20 +203,19 @@ class SNState:
             f32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32)
             d32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32)
             call("icgan_sn_prepare_weight", ptr(w), None, ptr(f32), ptr(d32), co, ci, k, L.F32, stream_ptr())
-            self.wk_fwd = torch.nn.functional.pad(f32, (0, 0, 0, 0, 0, 0, 0, self.co_pad)).to(torch.bfloat16)
-            self.wk_dgrad = torch.nn.functional.pad(d32, (0, self.co_pad)).to(torch.bfloat16).contiguous()
+            self._keep("wk_fwd", torch.nn.functional.pad(f32, (0, 0, 0, 0, 0, 0, 0, self.co_pad)).to(torch.bfloat16))
+            self._keep("wk_dgrad", torch.nn.functional.pad(d32, (0, self.co_pad)).to(torch.bfloat16))
             return
         if self.mode == "tc" and self.mode_d == "tc":  # both operands are plain bf16 relayouts: write them directly
-            self.wk_fwd = torch.empty(co, k, k, ci, device=w.device, dtype=torch.bfloat16)
-            self.wk_dgrad = torch.empty(ci, k, k, co, device=w.device, dtype=torch.bfloat16)
-            call("icgan_sn_prepare_weight", ptr(w), None, ptr(self.wk_fwd), ptr(self.wk_dgrad), co, ci, k, L.BF16,
-                 stream_ptr())
+            fwd = self._slot("wk_fwd", (co, k, k, ci), torch.bfloat16, w.device)
+            dgr = self._slot("wk_dgrad", (ci, k, k, co), torch.bfloat16, w.device)
+            call("icgan_sn_prepare_weight", ptr(w), None, ptr(fwd), ptr(dgr), co, ci, k, L.BF16, stream_ptr())
             return
         f32 = torch.empty(co, k, k, ci, device=w.device, dtype=torch.float32)
         d32 = torch.empty(ci, k, k, co, device=w.device, dtype=torch.float32)
         call("icgan_sn_prepare_weight", ptr(w), None, ptr(f32), ptr(d32), co, ci, k, L.F32, stream_ptr())
-        self.wk_fwd = self._operand(f32, self.mode, self.kp)
-        self.wk_dgrad = self._operand(d32, self.mode_d, self.kp_d)
+        self._keep("wk_fwd", self._operand(f32, self.mode, self.kp))
+        self._keep("wk_dgrad", self._operand(d32, self.mode_d, self.kp_d))
 
     def build_down_operands(self):
         """4x4 stride-2 kernel of avgpool2(conv3x3(.)) (DownConvFn), merged from the float32 master weight."""
@@ -192,9 +223,9 @@ class SNState:
         co, ci, k, _ = w.shape
         w9 = w.detach().permute(0, 2, 3, 1).reshape(co, 9, ci)
         dn = torch.einsum("tk,okc->otc", down_merge_matrix(w.device), w9)
-        self.wk_down = dn.to(torch.bfloat16).contiguous()                      # [Co, 16, Ci]
-        self.wk_down_d = dn.permute(2, 1, 0).to(torch.bfloat16).contiguous()   # [Ci, 16, Co]
-        self.down_version = (w._version, _WEIGHT_EPOCH[0])
+        self._keep("wk_down", dn.to(torch.bfloat16))                      # [Co, 16, Ci]
+        self._keep("wk_down_d", dn.permute(2, 1, 0).to(torch.bfloat16))   # [Ci, 16, Co]
+        self.down_version = weight_stamp(w)
 
     def build_up_operands(self):
         """Merged 2x2-phase slices of the sub-pixel up-convolution (UpConvFn), from the float32 master weight."""
@@ -202,9 +233,9 @@ class SNState:
         co, ci, k, _ = w.shape
         w9 = w.detach().permute(0, 2, 3, 1).reshape(co, 9, ci)
         up = torch.einsum("tk,okc->otc", up_merge_matrix(w.device), w9)
-        self.wk_up = up.to(torch.bfloat16).contiguous()                      # [Co, 16, Ci]
-        self.wk_up_d = up.permute(2, 1, 0).to(torch.bfloat16).contiguous()   # [Ci, 16, Co]
-        self.up_version = (w._version, _WEIGHT_EPOCH[0])
+        self._keep("wk_up", up.to(torch.bfloat16))                      # [Co, 16, Ci]
+        self._keep("wk_up_d", up.permute(2, 1, 0).to(torch.bfloat16))   # [Ci, 16, Co]
+        self.up_version = weight_stamp(w)
 
     def weight_grad(self, G: Tensor, snap=None) -> Tensor:
         """dL/dW (master layout) from G = dL/d(W/sigma) given in operand layout (float32); `snap` = the (v, u', sigma)

@@ -95,7 +95,7 @@ class FusedAdamEMA:
              float(self.ema_decay) if use_ema else -1.0, stream_ptr())
         self.grad_scale = 1.0
         from . import ops
-        ops.invalidate_operands()  # the conv operand copies of the master weights are stale now
+        ops.invalidate_operands(self)  # the conv operand copies of THESE master weights are stale now
 
     @property
     def state(self):
