@@ -864,22 +864,21 @@ def main():
     ops.PROFILE = None
     ms = e0.elapsed_time(e1) / args.steps
     prof_steps, prof_ms = args.steps, ms
-    if graphed and rank == 0:
+    if graphed:
         # per-kernel CUDA events cannot be recorded inside a graph: the tensor-core launches are timed in an eager,
-        # instrumented pass over the same step right after the timed region (same kernels, shapes and data)
+        # instrumented pass over the same step right after the timed region (same kernels, shapes and data).  Every rank
+        # runs it (the steps contain collectives); only rank 0 records events.
         prof_steps = min(args.steps, 3)
         step_dev(train_eager)  # the eager path's allocator pool is cold after the replays: one untimed step first
-        ops.PROFILE = []
+        ops.PROFILE = [] if rank == 0 else None
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
         for _ in range(prof_steps):
             step_dev(train_eager)
         p1.record()
-        torch.cuda.synchronize()
+        barrier()
         prof, ops.PROFILE = ops.PROFILE, None
         prof_ms = p0.elapsed_time(p1) / prof_steps
-    if world > 1:
-        barrier()
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
