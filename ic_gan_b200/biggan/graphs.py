@@ -64,10 +64,8 @@ class GraphedMicroSteps:
         self.launches[key] = _lib.LAUNCHES - before
 
     def _refresh_operands(self):
-        before = _lib.LAUNCHES
         for net in self.nets.values():
             net.prepare_operands()
-        return _lib.LAUNCHES - before
 
     def run(self, name: str, fn: Callable, **inputs):
         """fn(**inputs) -> tuple of tensors; later calls with inputs of the same shapes replay the captured graph and

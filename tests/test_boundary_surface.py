@@ -40,3 +40,33 @@ def test_signature_matches_reference(ref_name):
     for name, kind, default in mine[pos:]:  # extensions must be optional
         assert default != "<required>" or kind in ("VAR_KEYWORD", "VAR_POSITIONAL"), \
             f"{ref_name}: extra parameter `{name}` has no default"
+
+
+def test_operand_staleness_is_tracked_per_parameter():
+    """ops.weight_stamp: an optimiser step marks only ITS parameters stale (G's operand copies survive D's step); a call
+    without an optimiser invalidates everything.  Host logic only -- no kernels involved."""
+    import torch
+    from ic_gan_b200 import ops
+    a, b = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(3))
+    a.grad, b.grad = torch.ones(3), torch.ones(3)
+    sa, sb = ops.weight_stamp(a), ops.weight_stamp(b)
+    torch.optim.SGD([a], lr=0.1).step()          # the package registers a global post-step hook
+    assert ops.weight_stamp(a) != sa and ops.weight_stamp(b)[1:] == sb[1:]
+    sa, sb = ops.weight_stamp(a), ops.weight_stamp(b)
+    ops.invalidate_operands()
+    assert ops.weight_stamp(a) != sa and ops.weight_stamp(b) != sb
+
+
+def test_operand_buffers_are_rewritten_in_place():
+    """SNState._keep / _slot: operand copies keep their storage across rebuilds (a captured CUDA graph bakes the address)."""
+    import torch
+    from ic_gan_b200 import ops
+    st = ops.SNState(module=None, kind="conv")
+    first = st._keep("wk_fwd", torch.arange(6.0).reshape(2, 3).t())   # non-contiguous value -> stored densely
+    assert first.is_contiguous() and st.wk_fwd is first
+    again = st._keep("wk_fwd", torch.ones(3, 2))
+    assert again is first and float(first.sum()) == 6.0
+    other = st._keep("wk_fwd", torch.ones(4, 2))                        # a new shape gets a new buffer
+    assert other is not first and st.wk_fwd is other
+    slot = st._slot("wk_dgrad", (2, 2), torch.float32, torch.device("cpu"))
+    assert st._slot("wk_dgrad", (2, 2), torch.float32, torch.device("cpu")) is slot
