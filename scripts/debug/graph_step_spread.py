@@ -15,11 +15,11 @@ from tests.helpers import model_kwargs  # noqa: E402
 from tests.test_biggan_step import _check, _load  # noqa: E402
 
 
-def one(graphs, dev):
+def one(graphs, dev, cdt=torch.float32):
     meta, fx = _load()
     cfg, hp = O.BigGANConfig(**meta["config"]), meta["hp"]
     kw = model_kwargs(cfg)
-    okw = dict(adam_eps=hp["adam_eps"], compute_dtype=torch.float32)
+    okw = dict(adam_eps=hp["adam_eps"], compute_dtype=cdt)
     G = Generator(G_lr=hp["G_lr"], G_B1=hp["B1"], G_B2=hp["B2"], **okw, **kw)
     G_ema = Generator(no_optim=True, **okw, **kw)
     D = Discriminator(D_lr=hp["D_lr"], D_B1=hp["B1"], D_B2=hp["B2"], **okw, **kw)
@@ -48,6 +48,7 @@ def one(graphs, dev):
             print("   ", str(e)[:200])
     from oracle.step_fixture import sample_of
     upd_worst, upd_name = 0.0, ""
+    num = den = 0.0
     sd0 = {"G": O.synth_state_dict(meta["g_shapes"], hp["seed"]), "D": O.synth_state_dict(meta["d_shapes"], hp["seed"] + 1)}
     lr_of = {"G": hp["G_lr"], "D": hp["D_lr"]}
     for tag, net in (("G", G), ("D", D)):
@@ -58,9 +59,11 @@ def one(graphs, dev):
             if upd_ref.norm() < 0.05 * lr_of[tag] * upd_ref.numel() ** 0.5:
                 continue
             e = float((upd - upd_ref).norm() / upd_ref.norm())
+            num += float((upd - upd_ref).norm()) ** 2
+            den += float(upd_ref.norm()) ** 2
             if e > upd_worst:
                 upd_worst, upd_name = e, f"{tag}.{k}"
-    out.append((upd_worst, upd_name))
+    out.append((upd_worst, upd_name, (num / den) ** 0.5))
     worst_buf = 0.0
     for tag, net in (("G", G), ("D", D)):
         for k, b in net.named_buffers():
@@ -72,10 +75,11 @@ def one(graphs, dev):
 
 def main():
     dev = torch.device("cuda:0")
+    cdt = torch.bfloat16 if (len(sys.argv) > 1 and sys.argv[1] == "bf16") else torch.float32
     for graphs in (False, True, False, True, False, True, False, True):
-        g, d, e, u, b = one(graphs, dev)
+        g, d, e, u, b = one(graphs, dev, cdt)
         print(f"{'graphs' if graphs else 'eager '}: worst |w - w_ref| / lr  G {g:.3f}  D {d:.3f}  G_ema {e:.3f}   worst buffer {b:.2e}"
-              f"   worst per-tensor update rel-L2 {u[0]:.3e} ({u[1]})", flush=True)
+              f"   update rel-L2: worst tensor {u[0]:.3e} ({u[1]}), all tensors together {u[2]:.3e}", flush=True)
 
 
 if __name__ == "__main__":

@@ -122,7 +122,7 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs
     def update_error(tag, net_sd, sd0, lr):
         """worst per-tensor rel-L2 of (w_after - w_before) against the reference's update; tensors whose reference
         update is rounding noise (e.g. conv biases feeding a batch norm) are skipped."""
-        worst, worst_k = 0.0, ""
+        worst, worst_k, num, den = 0.0, "", 0.0, 0.0
         for k, w0 in sd0.items():
             if f"{tag}/{k}" not in fx or not O.is_param(k, net_sd[k]):
                 continue
@@ -130,10 +130,11 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs
             upd_ref = fx[f"{tag}/{k}"] - w0s
             if upd_ref.norm() < 0.05 * lr * upd_ref.numel() ** 0.5:
                 continue
-            e = float((sample_of(net_sd[k].detach().float().cpu()) - w0s - upd_ref).norm() / upd_ref.norm())
-            if e > worst:
-                worst, worst_k = e, f"{tag}.{k}"
-        return worst, worst_k
+            err = float((sample_of(net_sd[k].detach().float().cpu()) - w0s - upd_ref).norm())
+            num, den = num + err ** 2, den + float(upd_ref.norm()) ** 2
+            if err / float(upd_ref.norm()) > worst:
+                worst, worst_k = err / float(upd_ref.norm()), f"{tag}.{k}"
+        return worst, worst_k, (num / max(den, 1e-30)) ** 0.5
 
     if cdt == torch.float32:
         assert np.allclose(np.array(losses), ref_losses, atol=2e-3 * max(1.0, np.abs(ref_losses).max()))
@@ -142,9 +143,10 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs
         # into 1.4e-5 in the weights, G's gradient through that D differs by 2e-4, and from there the trajectory lands in
         # one of a few discrete branches.  Sixteen runs, eager and CUDA-graph mode alike (profiles/r02_step_parity_spread.txt):
         # worst well-conditioned element 0.003 .. 0.28 x lr in eleven of them, 1.1 .. 2.0 x lr in five; worst per-tensor
-        # update rel-L2 9e-4 .. 9.1e-2 in all of them.  So: every tensor's UPDATE within 0.25 rel-L2 of the reference's
-        # (a wrong schedule -- EMA start, accumulation, toggling, optimiser order -- changes updates by O(1)), and
-        # every element within the 3 x lr that three Adam steps can move it.
+        # update rel-L2 9e-4 .. 9.1e-2 in the eight runs that recorded it.  So: every tensor's UPDATE within 0.5 rel-L2 of
+        # the reference's and all tensors together within 0.25 (a skipped update is 1.0, a wrong schedule -- EMA start,
+        # accumulation, toggling, optimiser order -- changes updates by O(1)), and every element within the 3 x lr that
+        # three Adam steps can move it.
         wg = _check("G", G.state_dict(), fx, hp["G_lr"], 3.0, buf_tol=5e-3, hp=hp)
         wd = _check("D", D.state_dict(), fx, hp["D_lr"], 3.0, buf_tol=5e-3, hp=hp)
         we = _check("G_ema", G_ema.state_dict(), fx, hp["G_lr"], 3.0, buf_tol=5e-3, hp=hp)
@@ -153,30 +155,26 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs
         ud = update_error("D", D.state_dict(), d_sd0, hp["D_lr"])
         ue = update_error("G_ema", G_ema.state_dict(), g_sd0, hp["G_lr"])
         print(f"step fp32: worst per-tensor update rel-L2: G {ug[0]:.3e} ({ug[1]}), D {ud[0]:.3e} ({ud[1]}), "
-              f"G_ema {ue[0]:.3e} ({ue[1]})")
-        assert max(ug[0], ud[0], ue[0]) <= 0.25, (ug, ud, ue)
+              f"G_ema {ue[0]:.3e} ({ue[1]}); all tensors together G {ug[2]:.3e}, D {ud[2]:.3e}, G_ema {ue[2]:.3e}")
+        assert max(ug[0], ud[0], ue[0]) <= 0.5 and max(ug[2], ud[2], ue[2]) <= 0.25, (ug, ud, ue)
         for tag, net in (("G", G), ("D", D)):
             for k, p in net.named_parameters():
                 for mom in ("exp_avg", "exp_avg_sq"):
                     ref = fx[f"{tag}_{mom}/{k}"]
                     got = sample_of(net.optim.state[p][mom].float().cpu())
-                    assert (got - ref).norm() <= 0.25 * ref.norm() + 1e-5 * ref.numel() ** 0.5, f"{tag} {mom} {k}"
+                    # (halved gradients -- a dropped accumulation -- would be 0.5 / 0.75 off; the trajectory branches above
+                    # move the last step's gradients by a few per cent)
+                    assert (got - ref).norm() <= 0.35 * ref.norm() + 1e-5 * ref.numel() ** 0.5, f"{tag} {mom} {k}"
     else:
         # bf16 tensor-core mode: per-element agreement of an Adam update is not a meaningful bar (a gradient element whose
         # bf16 noise exceeds adam_eps moves by a different fraction of lr); hold the losses and the per-tensor UPDATE
         # direction instead: rel-L2 of (w_after - w_before) against the reference's update, worst tensor printed.
         assert np.allclose(np.array(losses), ref_losses, atol=0.05 * max(1.0, np.abs(ref_losses).max()))
-        worst, worst_k = 0.0, ""
-        lr_of = {"G": hp["G_lr"], "D": hp["D_lr"]}
-        for tag, net, sd0 in (("G", G, g_sd0), ("D", D, d_sd0)):
-            for k, p in net.named_parameters():
-                w0 = sample_of(sd0[k])
-                upd_ref = fx[f"{tag}/{k}"] - w0
-                upd = sample_of(p.detach().float().cpu()) - w0
-                if upd_ref.norm() < 0.05 * lr_of[tag] * upd_ref.numel() ** 0.5:
-                    continue  # gradient is rounding noise (e.g. conv biases feeding a batch norm): nothing to compare
-                e = float((upd - upd_ref).norm() / upd_ref.norm())
-                if e > worst:
-                    worst, worst_k = e, f"{tag}.{k}"
-        print(f"step bf16: worst per-tensor update rel-L2 {worst:.3e} ({worst_k})")
-        assert worst <= 0.6, f"{worst_k}: update rel-L2 {worst:.3e}"
+        ug = update_error("G", G.state_dict(), g_sd0, hp["G_lr"])
+        ud = update_error("D", D.state_dict(), d_sd0, hp["D_lr"])
+        print(f"step bf16: update rel-L2: worst tensor G {ug[0]:.3e} ({ug[1]}), D {ud[0]:.3e} ({ud[1]}); "
+              f"all tensors together G {ug[2]:.3e}, D {ud[2]:.3e}")
+        # Ten runs (profiles/r02_step_parity_spread.txt, eager and graph mode): all tensors together 0.169 .. 0.176; the
+        # worst single tensor is always a handful of elements (a bias of 16, the attention gamma scalar) and moves between
+        # 0.40 and 0.59 from run to run -- it is held below "update skipped" (1.0), the aggregate to 0.3.
+        assert max(ug[2], ud[2]) <= 0.3 and max(ug[0], ud[0]) <= 0.9, (ug, ud)
