@@ -134,7 +134,7 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs
             num, den = num + err ** 2, den + float(upd_ref.norm()) ** 2
             if err / float(upd_ref.norm()) > worst:
                 worst, worst_k = err / float(upd_ref.norm()), f"{tag}.{k}"
-        return worst, worst_k, (num / max(den, 1e-30)) ** 0.5
+        return worst, worst_k, (num / max(den, 1e-30)) ** 0.5, num, max(den, 1e-30)
 
     if cdt == torch.float32:
         assert np.allclose(np.array(losses), ref_losses, atol=2e-3 * max(1.0, np.abs(ref_losses).max()))
@@ -172,9 +172,10 @@ def test_gpu_training_function_matches_reference_golden(cuda_device, cdt, graphs
         assert np.allclose(np.array(losses), ref_losses, atol=0.05 * max(1.0, np.abs(ref_losses).max()))
         ug = update_error("G", G.state_dict(), g_sd0, hp["G_lr"])
         ud = update_error("D", D.state_dict(), d_sd0, hp["D_lr"])
+        together = ((ug[3] + ud[3]) / (ug[4] + ud[4])) ** 0.5  # every parameter of G and D as one vector
         print(f"step bf16: update rel-L2: worst tensor G {ug[0]:.3e} ({ug[1]}), D {ud[0]:.3e} ({ud[1]}); "
-              f"all tensors together G {ug[2]:.3e}, D {ud[2]:.3e}")
+              f"G {ug[2]:.3e}, D {ud[2]:.3e}, all tensors together {together:.3e}")
         # Ten runs (profiles/r02_step_parity_spread.txt, eager and graph mode): all tensors together 0.169 .. 0.176; the
         # worst single tensor is always a handful of elements (a bias of 16, the attention gamma scalar) and moves between
         # 0.40 and 0.59 from run to run -- it is held below "update skipped" (1.0), the aggregate to 0.3.
-        assert max(ug[2], ud[2]) <= 0.3 and max(ug[0], ud[0]) <= 0.9, (ug, ud)
+        assert together <= 0.3 and max(ug[0], ud[0]) <= 0.9, (together, ug, ud)
