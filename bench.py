@@ -831,7 +831,17 @@ def main():
         torch.cuda.synchronize()
 
     G.train(); D.train()
-    for _ in range(args.warmup):
+    warm = args.warmup
+    if graphed and warm > 0:
+        try:  # the first step captures the two micro-step graphs
+            step_dev()
+            torch.cuda.synchronize()
+        except Exception as exc:  # a capture problem must not take the measurement down: eager launches measure the same step
+            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); continuing with eager launches",
+                  file=sys.stderr, flush=True)
+            graphed, train_dev = False, train_eager
+        warm -= 1
+    for _ in range(warm):
         step_dev()
     barrier()
     if args.torch_profile:
