@@ -12,7 +12,7 @@
 //   attn_bwd_q_kernel  same tiling for the query-side backward:  P recomputed from the saved log-sum-exp,
 //                      dP = dO g^T (second TMEM accumulator), dS = P (dP - rowsum(dO o)) written as bf16 to shared memory
 //                      (operand of  dtheta += dS phi, third accumulator; phi is the tile already loaded for the logits, read
-//                      MN-major).  rowsum(dO o) is also written out for the key side.
+//                      MN-major).  rowsum(dO o) comes from a coalesced pre-pass (attn_rowdot_kernel) that also feeds the key side.
 //   attn_bwd_kv_kernel one CTA per 128 keys, walking the queries 64 at a time:  S^T = phi theta^T and dP^T = g dO^T
 //                      (double-buffered TMEM accumulators, thread = key row, the per-query log-sum-exp and rowsum arrive
 //                      with the stage as two 256-byte bulk copies), P^T and dS^T as bf16 K-major tiles in shared memory,
