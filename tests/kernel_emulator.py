@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY: a CPU emulation of the libicgan_b200 entry points the StyleGAN2 path calls, so that the HOST
+"""TEST INFRASTRUCTURE ONLY: a CPU emulation of the libicgan_b200 entry points the StyleGAN2 path (and the fused
+non-local block of the BigGAN path) calls, so that the HOST
 logic above the C ABI -- autograd closures (first and second order), tap tables of the strided / transposed tensor-core
 convolutions, layout handling, split-bf16 sequencing -- can be exercised in the CPU test suite, where no GPU exists.
 
@@ -236,11 +237,55 @@ def icgan_conv2d_wgrad_simt(x, dy, dwk, B, H, W, Ci, Co, k, stride, pad, in_dt, 
 def icgan_conv2d_wgrad_small(x, dy, dwk, B, H, W, Ci, Co, k, x_dt, dy_dt, stream):
     _wgrad_generic(x, dy, dwk, B, H, W, Ci, Co, k, 1, k // 2, x_dt, dy_dt)
 
+# ------------------------------------------------------------------------------------------------- fused non-local block
+_LOG2E = 1.4426950408889634
+
+
+def _attn_views(theta, phi, g, B, Q, Kk, d, dv):
+    t = _flat(theta, torch.bfloat16)[:B * Q * d].view(B, Q, d).float()
+    p = _flat(phi, torch.bfloat16)[:B * Kk * d].view(B, Kk, d).float()
+    v = _flat(g, torch.bfloat16)[:B * Kk * dv].view(B, Kk, dv).float()
+    return t, p, v
+
+
+def icgan_attn_fwd(theta, phi, g, o, lse2, B, Q, Kk, d, dv, stream):
+    t, p, v = _attn_views(theta, phi, g, B, Q, Kk, d, dv)
+    S = t @ p.transpose(1, 2)
+    _flat(o, torch.bfloat16)[:B * Q * dv].view(B, Q, dv).copy_((torch.softmax(S, -1) @ v).to(torch.bfloat16))
+    if lse2 is not None:
+        _flat(lse2, torch.float32)[:B * Q].view(B, Q).copy_(torch.logsumexp(S, -1) * _LOG2E)
+
+
+def _attn_ds(theta, phi, g, dout, lse2, dsum, B, Q, Kk, d, dv):
+    t, p, v = _attn_views(theta, phi, g, B, Q, Kk, d, dv)
+    do = _flat(dout, torch.bfloat16)[:B * Q * dv].view(B, Q, dv).float()
+    lse = _flat(lse2, torch.float32)[:B * Q].view(B, Q, 1)
+    P = torch.exp2((t @ p.transpose(1, 2)) * _LOG2E - lse)
+    dS = P * (do @ v.transpose(1, 2) - _flat(dsum, torch.float32)[:B * Q].view(B, Q, 1))
+    return t, p, do, P, dS
+
+
+def icgan_attn_bwd_q(theta, phi, g, o, dout, lse2, dtheta, ds, dsum, B, Q, Kk, d, dv, stream):
+    ov = _flat(o, torch.bfloat16)[:B * Q * dv].view(B, Q, dv).float()
+    do = _flat(dout, torch.bfloat16)[:B * Q * dv].view(B, Q, dv).float()
+    _flat(dsum, torch.float32)[:B * Q].view(B, Q).copy_((do * ov).sum(-1))     # the pre-pass of this call
+    t, p, do, P, dS = _attn_ds(theta, phi, g, dout, lse2, dsum, B, Q, Kk, d, dv)
+    _flat(dtheta, torch.bfloat16)[:B * Q * d].view(B, Q, d).copy_((dS @ p).to(torch.bfloat16))
+    if ds is not None:
+        _flat(ds, torch.bfloat16)[:B * Q * Kk].view(B, Q, Kk).copy_(dS.to(torch.bfloat16))
+
+
+def icgan_attn_bwd_kv(theta, phi, g, dout, lse2, dsum, dphi, dg, B, Q, Kk, d, dv, stream):
+    t, p, do, P, dS = _attn_ds(theta, phi, g, dout, lse2, dsum, B, Q, Kk, d, dv)
+    _flat(dphi, torch.bfloat16)[:B * Kk * d].view(B, Kk, d).copy_((dS.transpose(1, 2) @ t).to(torch.bfloat16))
+    _flat(dg, torch.bfloat16)[:B * Kk * dv].view(B, Kk, dv).copy_((P.transpose(1, 2) @ do).to(torch.bfloat16))
+
 
 EMULATED = {f.__name__: f for f in (
     icgan_modulate, icgan_chan_dot, icgan_bias_act_nhwc, icgan_bias_act, icgan_upfirdn2d, icgan_upfirdn2d_nhwc,
     icgan_conv2d_tc_ex, icgan_conv2d_tc, icgan_conv2d_wgrad_tc_ex, icgan_conv2d_wgrad_tc, icgan_conv2d_simt,
-    icgan_conv2d_small, icgan_conv2d_wgrad_simt, icgan_conv2d_wgrad_small)}
+    icgan_conv2d_small, icgan_conv2d_wgrad_simt, icgan_conv2d_wgrad_small, icgan_attn_fwd, icgan_attn_bwd_q,
+    icgan_attn_bwd_kv)}
 
 
 @contextlib.contextmanager
@@ -250,6 +295,7 @@ def emulated(monkeypatch):
     import ic_gan_b200.stylegan2.ops.conv2d_gradfix as m2
     import ic_gan_b200.stylegan2.ops.elementwise as m3
     import ic_gan_b200.stylegan2.ops.upfirdn2d as m4
+    import ic_gan_b200.ops as m5
 
     def call(name, *args):
         if name not in EMULATED:
@@ -257,7 +303,7 @@ def emulated(monkeypatch):
         with torch.no_grad():
             EMULATED[name](*args)
 
-    for m in (_lib, m1, m2, m3, m4):
+    for m in (_lib, m1, m2, m3, m4, m5):
         for attr, fn in (("call", call), ("ptr", _ptr), ("stream_ptr", lambda: None)):
             if hasattr(m, attr):
                 monkeypatch.setattr(m, attr, fn)

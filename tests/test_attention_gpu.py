@@ -17,7 +17,7 @@ SHAPES = [
 
 
 def _rel(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.detach().double(), b.detach().double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
